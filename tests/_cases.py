@@ -1,0 +1,48 @@
+"""Shared helpers: load a golden fixture and rebuild its kernel object (oracle.kernels stand-ins)."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import kernels as ok
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["matern6d_rest", "matern6d_pow2", "rbf2d_branin", "rbf_ard5d", "ising24_hamming", "tanimoto256",
+         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d"]
+LOOP_CASES = [c for c in CASES if c not in ("direct_branch", "tiny_passthrough")]
+
+
+def objective(x):
+    return torch.sin(3.0 * x).sum(-1) + (x ** 2).sum(-1)
+
+
+class Case:
+    def __init__(self, name, device="cpu"):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.name = name
+        self.raw = z
+        self.device = torch.device(device)
+        t = lambda k: torch.from_numpy(z[k].astype(np.float64) if z[k].dtype == np.uint8 else z[k]).to(self.device)
+        self.X, self.Z = t("X"), t("Z")
+        self.mu = t("mu") if "mu" in z else None
+        self.b = int(z["b"])
+        self.fam, self.mode = str(z["fam"]), str(z["mode"])
+        self.ls = z["ls"].tolist() or None
+        self.os = float(z["os"])
+        self.objective = objective if bool(z["objective"]) else None
+        self.idx, self.w = t("idx"), t("w")
+        self.U = t("U")
+        self.K_raw = t("K_raw")
+        self.n_car = int(z["n_car"])
+        self.Xobs = t("Xobs") if "Xobs" in z else None
+        self.noise = float(z["noise"]) if "noise" in z else None
+        self._t = t
+
+    def car(self, i, key):
+        return self._t("car%d_%s" % (i, key))
+
+    def kernel(self):
+        cov = ok.make_kernel(self.fam, self.ls if self.ls is not None else 1.0, self.os).to(self.device)
+        if self.mode == "kernel":
+            return ok.Kernel(ok.BareModel(cov), mode="kernel")
+        return ok.Kernel(ok.GPModel(cov, self.Xobs, None, noise=self.noise), mode=self.mode)
