@@ -1,0 +1,163 @@
+/*
+ * sober_b200 -- C ABI of the B200 (sm_100a) implementation of SOBER's RCHQ batch-selection hot path.
+ *
+ * Plain C: raw DEVICE pointers, sizes and a cudaStream_t (passed as void*).  No torch types, no
+ * allocation, no exceptions, no Python.  Every function returns SOBER_OK (0) or an error code and only
+ * ENQUEUES work on `stream` (no host synchronisation) unless stated otherwise.
+ *
+ * The reference is pure Python/PyTorch (no FFI of its own), so each entry point cites the lines of the
+ * reference it replaces; INTEGRATION.md shows the ctypes binding and how `SOBER/_rchq.py` is rebound.
+ *
+ * All floating-point data is IEEE binary64 ("f64"); alive-lists are int32 row ids (N < 2^31).
+ * Matrices are row-major.
+ */
+#ifndef SOBER_B200_H
+#define SOBER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOBER_B200_ABI_VERSION 1
+
+enum sober_status {
+    SOBER_OK = 0,
+    SOBER_ERR_ARG = 1,         /* inconsistent sizes / null pointers */
+    SOBER_ERR_CUDA = 2,        /* a CUDA runtime call failed (see sober_last_cuda_error) */
+    SOBER_ERR_UNSUPPORTED = 3, /* shape or family outside what the kernels cover */
+    SOBER_ERR_WORKSPACE = 4    /* workspace too small */
+};
+
+/* Kernel families: the base kernels reachable through SOBER/_kernel.py:16-30 in the examples --
+ * gpytorch ScaleKernel(RBFKernel | MaternKernel(nu)) and SOBER/_drug_modelling.py:15-25,86-101. */
+enum sober_family {
+    SOBER_RBF = 0,      /* exp(-d2/2)                                  d2 = |u-v|^2, u=(x-c)/l            */
+    SOBER_MATERN12 = 1, /* exp(-r)                                     r  = sqrt(max(d2,1e-30))           */
+    SOBER_MATERN32 = 2, /* (1+sqrt3 r) exp(-sqrt3 r)                                                      */
+    SOBER_MATERN52 = 3, /* (1+sqrt5 r+5/3 r^2) exp(-sqrt5 r)                                              */
+    SOBER_TANIMOTO = 4  /* max(0,(<x,z>+1e-6)/(1e-6+|x|^2+|z|^2-<x,z>))                                   */
+};
+
+int sober_abi_version(void);
+/* Text of the last CUDA error seen by this library on the calling thread ("" if none). */
+const char* sober_last_cuda_error(void);
+/* Number of SMs of the current device (grid sizing on the host side). */
+int sober_sm_count(int* out);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Streaming preparation passes (HBM-bound).
+ * ------------------------------------------------------------------------------------------------- */
+
+/* Stationary families.  P[i, k] = (X[i, k] - center[k]) * inv_ls[k] for k < d and P[i, d] = sum_k P[i,k]^2.
+ * `ldp` >= d + 1 (the pad, if any, is zeroed).  Replaces the per-call `x1.div(lengthscale)` / centring of
+ * gpytorch's RBF/Matern forward reached from SOBER/_rchq.py:124.  X: n x d, row stride ldx. */
+int sober_prepare_points(const double* X, int64_t ldx, int64_t n, int32_t d, const double* center,
+                         const double* inv_ls, double* P, int64_t ldp, void* stream);
+
+/* out[i] = sum_k X[i,k]^2  (Tanimoto |x|^2, SOBER/_drug_modelling.py:21-22). */
+int sober_row_sqnorm(const double* X, int64_t ldx, int64_t n, int32_t d, double* out, void* stream);
+
+/* Stable compaction of the non-zero weights: `idx_story = arange(N)[mu != 0]` (SOBER/_rchq.py:63-65).
+ * Writes ascending row ids to idx_out, their weights to mu_out and the count to *count_out (device).
+ * workspace: at least sober_compact_workspace(n) bytes. */
+int64_t sober_compact_workspace(int64_t n);
+int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_out, double* mu_out, int64_t* count_out,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K1: fused cross-kernel + weighted strided group sums  (SOBER/_rchq.py:116-136,152; also :35,:78 as a
+ * plain Gram when S = number of points and a single row).
+ *
+ *   At[g, l]  = outputscale * sum_{rows e} k(z_l, x_{e*S+g}) * mu_{e*S+g}       over ALL valid positions
+ *   totw[g]   =               sum_{rows e, e*S+g < ES} mu_{e*S+g}
+ *
+ * A "position" p is the rank of a point in the global ascending alive-list; this device owns positions
+ * [pos0, pos0 + n_local).  Position p belongs to group p mod S.  Positions >= ES (the remainder of
+ * SOBER/_rchq.py:128-136) are accumulated into At (column p - ES, "the quirk") but not into totw.
+ * Never materialises the (E, L, S) Gram of SOBER/_rchq.py:124.
+ *
+ * X / ldx / xn / xn_stride: candidate rows and their squared norms (for stationary families the output of
+ *   sober_prepare_points: xn = P + d, xn_stride = ldp; for Tanimoto the raw rows and sober_row_sqnorm).
+ * idx: local alive-list (row ids into X), NULL = identity.   mu: weights aligned with idx, NULL = 1.
+ * Zt (L x d): landmark table -- stationary: -2 (z - c) * inv_ls ; Tanimoto: z.   zn (L): |.|^2 of the same.
+ * At: S x L (transposed on purpose: coalesced stores and it is the left operand of the projection).
+ * workspace holds the per-split partial sums (deterministic two-stage reduction, no atomics).
+ * variant: 0 = automatic, 1 = force the generic tiled kernel, 2 = force the small-d register kernel.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct sober_group_args {
+    const double* X;
+    int64_t ldx;
+    const double* xn;
+    int64_t xn_stride;
+    const int32_t* idx;
+    const double* mu;
+    int64_t n_local;
+    int64_t pos0;
+    int64_t n_global;
+    int64_t ES;
+    int32_t S;
+    int32_t L;
+    int32_t d;
+    int32_t family;
+    double outputscale;
+    const double* Zt;
+    const double* zn;
+    double* At;
+    double* totw;
+    int32_t variant;
+    int32_t reserved;
+} sober_group_args;
+
+int64_t sober_group_accumulate_workspace(const sober_group_args* args);
+int sober_group_accumulate(const sober_group_args* args, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Same reduction when the Gram tile has been produced by an opaque callable (generic-kernel path):
+ *   At[g, l] += sum_{j : (pos_begin + j) mod S == g} G[l, j] * mu[j],   totw likewise for positions < ES.
+ * G: L x m row-major (ldg).  (SOBER/_rchq.py:124-126 with `kernel` a black box.) */
+int sober_group_accumulate_gram(const double* G, int64_t ldg, int32_t L, int64_t m, const double* mu,
+                                int64_t pos_begin, int64_t ES, int32_t S, double* At, double* totw,
+                                void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * CAR elimination (SOBER/_rchq.py:237-266) on a given null-space basis.
+ *   basis: k x S row-major, row c = column c of Phi (i.e. `Vh[-(N-n):, :]` as torch returns it).
+ *          DESTROYED (used as the publish buffer).
+ *   mu:    S weights, updated in place to the reduced measure (zeros at eliminated positions).
+ *   pivots_out (k int32, may be NULL): eliminated position per step, -1 after an early stop.
+ *   steps_out (1 int32, may be NULL): number of steps taken.
+ * Arithmetic order is the reference's (unfused mul / div / sub), so given the same basis the pivots are
+ * bit-identical.  Persistent cooperative kernel: sync_ws needs sober_car_workspace(k) bytes (zeroed by
+ * the call).
+ * ------------------------------------------------------------------------------------------------- */
+int64_t sober_car_workspace(int32_t k);
+int sober_car_eliminate(double* basis, int32_t k, int32_t S, double* mu, int32_t* pivots_out, int32_t* steps_out,
+                        void* sync_ws, int64_t sync_ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Weight update + compaction of the alive-list (SOBER/_rchq.py:198-221).
+ *   For local position j (global p = pos0 + j):
+ *     p <  ES: g = p mod S; kept iff wstar[g] > 0; new global position q = (p / S) * K + rank[g]
+ *     p >= ES: kept iff tail_keep;                  q = (ES / S) * K + (p - ES)
+ *     kept:    mu_out[q - new_pos0] = (mu_in[j] * wstar[g]) / totw[g]      (g = S-1 for the tail)
+ *              idx_out[q - new_pos0] = idx_in[j]
+ *   rank[g] = number of kept groups below g, K = number of kept groups (both computed by the caller).
+ * ------------------------------------------------------------------------------------------------- */
+int sober_update_compact(const int32_t* idx_in, const double* mu_in, int64_t n_local, int64_t pos0, int64_t ES,
+                         int32_t S, const double* wstar, const double* totw, const int32_t* rank, int32_t K,
+                         int32_t tail_keep, int64_t new_pos0, int32_t* idx_out, double* mu_out, void* stream);
+
+/* dst[:] = 0 ; dst[idx[j]] = w[j]   -- the in-place sparse result of SOBER/_rchq.py:109-110. */
+int sober_scatter_result(double* dst, int64_t n, const int64_t* idx, const double* w, int64_t m, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Diagnostics: FP64 FMA throughput probe (the roofline denominator for K1, which is FP64-pipe bound).
+ * Launches `blocks` x 256 threads, each doing iters * 8 dependent-chain DFMAs; flops = blocks*256*iters*16.
+ * ------------------------------------------------------------------------------------------------- */
+int sober_fp64_probe(int32_t blocks, int64_t iters, double* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOBER_B200_H */

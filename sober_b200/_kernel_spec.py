@@ -1,0 +1,108 @@
+"""Introspection of the reference's kernel objects into a plain description the CUDA path can fuse.
+
+The reference hands ``recombination`` an opaque callable (``SOBER/_rchq.py:9``).  In every example it is a
+``SOBER._kernel.Kernel(model, mode)`` (``SOBER/_kernel.py:4-30``) around a gpytorch model whose
+``covar_module`` is ``ScaleKernel(RBFKernel | MaternKernel)`` or ``ScaleKernel(TanimotoKernel)``
+(``SOBER/_drug_modelling.py:86-107``).  Those objects stay untouched; this module only *reads* them
+(duck-typed on class names and attributes, so real gpytorch modules and the test stand-ins both work).
+
+Anything that cannot be described returns ``None`` and the caller takes the generic path, where the callable
+itself is evaluated tile by tile on the device.
+"""
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class KernelSpec:
+    family: int                      # _lib.RBF ... _lib.TANIMOTO
+    d: Optional[int]                 # input dimension if the lengthscale pins it (ARD), else None
+    inv_ls: Optional[torch.Tensor]   # (d,) or (1,) reciprocal lengthscales; None for Tanimoto
+    outputscale: float
+    mode: str                        # "kernel" | "predictive_covariance"
+    x_obs: Optional[torch.Tensor] = None     # (n_obs, d) training inputs      (predictive covariance)
+    woodbury: Optional[torch.Tensor] = None  # (n_obs, n_obs)  S S^T           (SOBER/_gp.py:255-278)
+
+    @property
+    def stationary(self):
+        return self.family != _lib.TANIMOTO
+
+
+def _cls(obj):
+    return type(obj).__name__
+
+
+def _describe_covar(covar):
+    """-> (family, inv_ls, outputscale) or None."""
+    outputscale = 1.0
+    base = covar
+    if _cls(covar) == "ScaleKernel":
+        os_ = covar.outputscale
+        if torch.is_tensor(os_):
+            if os_.numel() != 1:
+                return None          # batched kernels: generic path
+            os_ = float(os_.detach().reshape(-1)[0])
+        outputscale = float(os_)
+        base = covar.base_kernel
+    if getattr(base, "active_dims", None) is not None:
+        return None
+    name = _cls(base)
+    if name == "TanimotoKernel":
+        return _lib.TANIMOTO, None, outputscale
+    if name in ("RBFKernel", "MaternKernel"):
+        ls = base.lengthscale
+        if not torch.is_tensor(ls) or ls.dim() > 2 or (ls.dim() == 2 and ls.shape[0] != 1):
+            return None
+        inv_ls = (1.0 / ls.detach().to(torch.float64)).reshape(-1)
+        if name == "RBFKernel":
+            return _lib.RBF, inv_ls, outputscale
+        nu = float(base.nu)
+        fam = {0.5: _lib.MATERN12, 1.5: _lib.MATERN32, 2.5: _lib.MATERN52}.get(nu)
+        if fam is None:
+            return None
+        return fam, inv_ls, outputscale
+    return None
+
+
+def _covariance_cache(model):
+    """``get_cov_cache`` of SOBER/_gp.py:255-278: W = S S^T with S the prediction strategy's covar cache."""
+    x_obs = model.train_inputs[0]
+    try:
+        root = model.prediction_strategy.covar_cache
+    except Exception:
+        model.eval()
+        model(x_obs[0].unsqueeze(0))
+        root = model.prediction_strategy.covar_cache
+    root = root.detach()
+    return root @ root.T, x_obs.detach()
+
+
+def introspect(kernel) -> Optional[KernelSpec]:
+    model = getattr(kernel, "model", None)
+    mode = getattr(kernel, "mode", None)
+    if model is None or mode not in ("kernel", "predictive_covariance"):
+        return None
+    covar = getattr(model, "covar_module", None)
+    if covar is None:
+        return None
+    desc = _describe_covar(covar)
+    if desc is None:
+        return None
+    family, inv_ls, outputscale = desc
+    if not math.isfinite(outputscale):
+        return None
+    d = None
+    if inv_ls is not None and inv_ls.numel() > 1:
+        d = int(inv_ls.numel())
+    spec = KernelSpec(family, d, inv_ls, outputscale, mode)
+    if mode == "predictive_covariance":
+        try:
+            spec.woodbury, spec.x_obs = _covariance_cache(model)
+        except Exception:
+            return None
+    return spec

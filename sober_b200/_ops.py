@@ -1,0 +1,158 @@
+"""Device operations of the recombination loop: torch tensors in, C-ABI calls out.
+
+``CudaOps`` is the only implementation shipped.  It requires a CUDA device and the built extension and raises
+otherwise (no CPU fallback).  Tensors are allocated by torch (caching allocator), kernels are enqueued on
+torch's current stream; nothing here synchronises except where a count has to reach the host.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GroupArgs, check
+
+_FAMILY_NAMES = {"rbf": _lib.RBF, "matern12": _lib.MATERN12, "matern32": _lib.MATERN32,
+                 "matern52": _lib.MATERN52, "tanimoto": _lib.TANIMOTO}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class PointSet:
+    """Candidate (or landmark-as-candidate) rows in the layout K1 reads: ``rows`` (n x ld), ``xn`` view."""
+
+    def __init__(self, rows, ld, xn, xn_stride, n, d):
+        self.rows, self.ld, self.xn, self.xn_stride, self.n, self.d = rows, ld, xn, xn_stride, n, d
+
+
+class LandmarkTable:
+    """``Zt`` (L x d) and ``zn`` (L) as K1 wants them, plus the family / output scale."""
+
+    def __init__(self, zt, zn, family, outputscale):
+        self.zt, self.zn, self.family, self.outputscale = zt, zn, family, float(outputscale)
+        self.L, self.d = zt.shape
+
+
+class CudaOps:
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.SoberB200Error(
+                "sober_b200 needs a CUDA device (B200, sm_100a); there is no CPU implementation of the hot path")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.variant = 0
+        self._ws = None
+
+    # -- helpers -------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def f64(self, t):
+        return t.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
+
+    # -- streaming passes ------------------------------------------------------------------------------
+    def prepare_points(self, X, center, inv_ls):
+        """(X - c) * inv_ls with the squared norm appended: the candidate layout for stationary families."""
+        n, d = X.shape
+        ldp = (d + 1 + 1) // 2 * 2  # even row stride keeps rows 16-byte aligned
+        P = torch.empty((n, ldp), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_prepare_points(_ptr(X), X.stride(0), n, d, _ptr(center), _ptr(inv_ls), _ptr(P), ldp,
+                                                self._stream()), "prepare_points")
+        return PointSet(P, ldp, P[:, d], ldp, n, d)
+
+    def raw_points(self, X):
+        """Tanimoto layout: the rows as they are plus |x|^2."""
+        n, d = X.shape
+        xn = torch.empty(n, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_row_sqnorm(_ptr(X), X.stride(0), n, d, _ptr(xn), self._stream()), "row_sqnorm")
+        return PointSet(X, X.stride(0), xn, 1, n, d)
+
+    def compact_nonzero(self, mu):
+        """``arange(N)[mu != 0]`` and the matching weights; returns (idx int32, mu, count) -- one host sync."""
+        n = mu.numel()
+        idx = torch.empty(n, dtype=torch.int32, device=self.device)
+        out = torch.empty(n, dtype=torch.float64, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        nbytes = self.lib.sober_compact_workspace(n)
+        ws = self._workspace(nbytes)
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_compact_nonzero(_ptr(mu), n, _ptr(idx), _ptr(out), _ptr(cnt), _ptr(ws), ws.numel(),
+                                                 self._stream()), "compact_nonzero")
+        r = int(cnt.item())
+        return idx[:r], out[:r], r
+
+    # -- K1 ------------------------------------------------------------------------------------------------
+    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None):
+        """At (S x L) and totw (S) for the positions [pos0, pos0 + n_local) this device owns."""
+        At = torch.empty((S, lm.L), dtype=torch.float64, device=self.device)
+        totw = torch.empty(S, dtype=torch.float64, device=self.device)
+        a = GroupArgs()
+        a.X, a.ldx = pts.rows.data_ptr(), pts.ld
+        a.xn, a.xn_stride = pts.xn.data_ptr(), pts.xn_stride
+        a.idx = None if idx is None else idx.data_ptr()
+        a.mu = None if mu is None else mu.data_ptr()
+        a.n_local, a.pos0, a.ES = int(n_local), int(pos0), int(ES)
+        a.n_global = int(pos0 + n_local if n_global is None else n_global)
+        a.S, a.L, a.d, a.family = int(S), int(lm.L), int(lm.d), int(lm.family)
+        a.outputscale = lm.outputscale
+        a.Zt, a.zn = lm.zt.data_ptr(), lm.zn.data_ptr()
+        a.At, a.totw = At.data_ptr(), totw.data_ptr()
+        a.variant = self.variant
+        nbytes = self.lib.sober_group_accumulate_workspace(C.byref(a))
+        if nbytes < 0:
+            raise _lib.SoberB200Error("sober_b200: group_accumulate: bad arguments")
+        ws = self._workspace(nbytes)
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_group_accumulate(C.byref(a), _ptr(ws), ws.numel(), self._stream()),
+                  "group_accumulate")
+        return At, totw
+
+    def group_accumulate_gram(self, G, mu, pos_begin, ES, S, At, totw):
+        L, m = G.shape
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_group_accumulate_gram(_ptr(G), G.stride(0), L, m, _ptr(mu), int(pos_begin), int(ES),
+                                                       int(S), _ptr(At), _ptr(totw), self._stream()),
+                  "group_accumulate_gram")
+
+    # -- CAR -----------------------------------------------------------------------------------------------
+    def car_eliminate(self, basis_rows, mass, want_pivots=False):
+        """Runs the elimination in place on ``mass`` (S,); ``basis_rows`` (k x S, contiguous) is destroyed."""
+        k, S = basis_rows.shape
+        assert basis_rows.is_contiguous() and mass.is_contiguous()
+        piv = torch.empty(max(k, 1), dtype=torch.int32, device=self.device) if want_pivots else None
+        steps = torch.zeros(1, dtype=torch.int32, device=self.device) if want_pivots else None
+        nbytes = self.lib.sober_car_workspace(k)
+        flags = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_car_eliminate(_ptr(basis_rows), k, S, _ptr(mass), _ptr(piv), _ptr(steps), _ptr(flags),
+                                               flags.numel() * 4, self._stream()), "car_eliminate")
+        return (piv, steps) if want_pivots else None
+
+    # -- update + compaction ----------------------------------------------------------------------------------
+    def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out):
+        idx_out = torch.empty(n_out, dtype=torch.int32, device=self.device)
+        mu_out = torch.empty(n_out, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_update_compact(_ptr(idx), _ptr(mu), int(n_local), int(pos0), int(ES), int(S),
+                                                _ptr(wstar), _ptr(totw), _ptr(rank), int(K), int(bool(tail_keep)),
+                                                int(new_pos0), _ptr(idx_out), _ptr(mu_out), self._stream()),
+                  "update_compact")
+        return idx_out, mu_out
+
+    def scatter_result(self, dst, idx, w):
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_scatter_result(_ptr(dst), dst.numel(), _ptr(idx), _ptr(w), idx.numel(),
+                                                self._stream()), "scatter_result")
+
+    def fp64_probe(self, blocks, iters):
+        sink = torch.zeros(1, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.sober_fp64_probe(int(blocks), int(iters), _ptr(sink), self._stream()), "fp64_probe")

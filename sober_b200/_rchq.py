@@ -1,0 +1,359 @@
+"""Drop-in for ``SOBER/_rchq.py``: same ``recombination(...)`` signature and ``(idx, w)`` contract
+(SOBER/_rchq.py:5-31), B200-native execution.
+
+Host logic (this file) mirrors the control flow of ``Mod_Tchernychova_Lyons`` (SOBER/_rchq.py:51-221); every
+pass over the candidates is a hand-written sm_100a kernel reached through the C ABI (``_ops.CudaOps``):
+
+  reference                                   here
+  ------------------------------------------  --------------------------------------------------------------
+  idx_story = arange(N)[mu != 0]     :63-65   ops.compact_nonzero            (stream compaction)
+  kernel(pt_nys, samp[idx]) * mu, sum :124-136 ops.group_accumulate           (K1: never materialises (E,L,S))
+  U_svd @ X_for_nys, / tot_weights   :148-166 one small GEMM  At @ Uext^T     (landmarks stacked for pred. cov.)
+  Tchernychova_Lyons_CAR             :224-270 _car.caratheodory               (persistent elimination kernel)
+  mu updates + idx_story rebuild     :198-221 ops.update_compact              (closed-form scatter, no scan)
+
+The alive-list is kept COMPACT (row ids + weights of surviving points, ascending); "position" = rank in that
+list, group = position mod S, exactly the reshape of SOBER/_rchq.py:118-123.  With ``torch.distributed``
+enabled (``sober_b200.distributed``) candidates are row-sharded: each rank owns a contiguous range of positions
+and the only collective per iteration is one all-reduce of the (S x L') accumulator.
+"""
+import torch
+
+from . import _car, _nystrom, _psd
+from ._kernel_spec import introspect
+from ._ops import LandmarkTable
+from ._settings import options
+
+
+# ---------------------------------------------------------------------------------------------------------
+# communication: nothing for one GPU, torch.distributed when sharded
+# ---------------------------------------------------------------------------------------------------------
+class SingleProcess:
+    rank, world = 0, 1
+
+    def all_reduce(self, tensor):
+        return tensor
+
+    def all_gather_ints(self, value, device):
+        return [int(value)]
+
+
+class Sharded:
+    """Row-sharded candidates over a torch.distributed group (NCCL on the GPU box, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def all_reduce(self, tensor):
+        self.dist.all_reduce(tensor, group=self.group)
+        return tensor
+
+    def all_gather_ints(self, value, device):
+        mine = torch.tensor([int(value)], dtype=torch.int64, device=device)
+        out = torch.empty(self.world, dtype=torch.int64, device=device)
+        self.dist.all_gather_into_tensor(out, mine, group=self.group)
+        return [int(v) for v in out.tolist()]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# closed-form survivor counting (replaces the boolean-mask bookkeeping of SOBER/_rchq.py:198-221)
+# ---------------------------------------------------------------------------------------------------------
+class KeepMap:
+    """Which positions survive an iteration, given the kept groups.  All host-side integers."""
+
+    def __init__(self, kept_mask, S, ES):
+        self.S, self.ES, self.E = S, ES, ES // S
+        self.cum = [0] * (S + 1)                 # cum[g] = number of kept groups below g
+        for g in range(S):
+            self.cum[g + 1] = self.cum[g] + (1 if kept_mask[g] else 0)
+        self.K = self.cum[S]
+        self.tail_keep = bool(kept_mask[S - 1])
+
+    def before(self, p):
+        """Number of surviving positions strictly below global position p."""
+        if p <= self.ES:
+            return (p // self.S) * self.K + self.cum[p % self.S]
+        return self.E * self.K + ((p - self.ES) if self.tail_keep else 0)
+
+
+class Recombiner:
+    def __init__(self, ops, comm=None, opts=None, nullspace=None, basis=None, trace=None):
+        self.ops = ops
+        self.comm = comm or SingleProcess()
+        self.opts = opts or options
+        self.nullspace = nullspace        # test hook: design -> (k x S) rows
+        self.basis = basis                # test hook: use this Nystrom basis U (n x L) instead of computing it
+        self.trace = trace                # test hook: trace(stage, dict) with per-iteration intermediates
+
+    # -----------------------------------------------------------------------------------------------------
+    # landmarks / Nystrom block
+    # -----------------------------------------------------------------------------------------------------
+    def _table(self, pts, spec, center, inv_ls):
+        """LandmarkTable for raw landmark rows ``pts`` (L' x d)."""
+        if spec.stationary:
+            v = (pts - center) * inv_ls
+            return LandmarkTable((-2.0 * v).contiguous(), (v * v).sum(-1).contiguous(), spec.family, spec.outputscale)
+        return LandmarkTable(pts.contiguous(), (pts * pts).sum(-1).contiguous(), spec.family, spec.outputscale)
+
+    def _points(self, X, spec, center, inv_ls):
+        return self.ops.prepare_points(X, center, inv_ls) if spec.stationary else self.ops.raw_points(X)
+
+    def _gram_T(self, pointset, table):
+        """k(table, points)^T as an (m x L) matrix: K1 with one row of m singleton groups and unit weights."""
+        m = pointset.n
+        at, _ = self.ops.group_accumulate(pointset, table, None, None, m, 0, 0, m)
+        return at
+
+    def _nystrom(self, Z, n_basis, kernel, spec, center, inv_ls):
+        """-> U (n x L), Uext (n x L'), landmark table over L' = L (+ n_obs) stacked landmarks."""
+        o = self.opts
+        table = uext_tail = None
+        k_zo_w = None
+        if spec is not None:
+            table_z = self._table(Z, spec, center, inv_ls)
+            table = table_z
+            if spec.mode == "predictive_covariance":
+                x_obs = self.ops.f64(spec.x_obs)
+                w = self.ops.f64(spec.woodbury)
+                k_oz = self._gram_T(self._points(x_obs, spec, center, inv_ls), table_z)     # (n_obs x L)
+                k_zo_w = k_oz.T @ w                                                          # (L x n_obs)
+                table = self._table(torch.cat([Z, x_obs], 0), spec, center, inv_ls)
+        if self.basis is not None:
+            U = self.ops.f64(self.basis)
+        elif spec is not None and o.gram == "cuda":
+            gram = self._gram_T(self._points(Z, spec, center, inv_ls), table_z)              # (L x L)
+            if k_zo_w is not None:
+                gram = gram - k_zo_w @ k_oz
+            gram = 0.5 * (gram + gram.T)
+            gram = _psd.repair(gram, o.gate, assume_asymmetric=True)
+            U = _nystrom.lowrank_basis(gram, n_basis)
+        else:
+            gram = kernel(Z, Z)
+            gram = _psd.repair(gram, o.gate)
+            U = _nystrom.lowrank_basis(gram, n_basis)
+        if k_zo_w is not None:
+            uext_tail = -(U @ k_zo_w)
+        Uext = U if uext_tail is None else torch.cat([U, uext_tail], 1)
+        return U, Uext.contiguous(), table
+
+    # -----------------------------------------------------------------------------------------------------
+    # one K1 pass over the local alive-list (fused kernel or generic callable)
+    # -----------------------------------------------------------------------------------------------------
+    def _accumulate(self, st, idx, mu, n_local, pos0, ES, S):
+        if st["spec"] is not None:
+            return self.ops.group_accumulate(st["pts"], st["table"], idx, mu, n_local, pos0, ES, S)
+        L = st["Z"].shape[0]
+        dev = self.ops.device
+        at = torch.zeros((S, L), dtype=torch.float64, device=dev)
+        totw = torch.zeros(S, dtype=torch.float64, device=dev)
+        step = max(int(self.opts.generic_chunk), 1)
+        for c0 in range(0, n_local, step):
+            c1 = min(n_local, c0 + step)
+            rows = st["X"][idx[c0:c1].long()] if idx is not None else st["X"][c0:c1]
+            tile = st["kernel"](st["Z"], rows).to(torch.float64).contiguous()
+            self.ops.group_accumulate_gram(tile, None if mu is None else mu[c0:c1], pos0 + c0, ES, S, at, totw)
+        return at, totw
+
+    # -----------------------------------------------------------------------------------------------------
+    def run(self, pts_rec, pts_nys, num_pts, kernel, init_weights=None, calc_obj=None):
+        ops, comm, o = self.ops, self.comm, self.opts
+        dev = ops.device
+        X = ops.f64(pts_rec)
+        Z = ops.f64(pts_nys)
+        if X.dim() != 2 or Z.dim() != 2 or X.shape[1] != Z.shape[1]:
+            raise ValueError("pts_rec (N, d) and pts_nys (L, d) must be 2-D with the same d")
+        n_rows = X.shape[0]
+        counts = comm.all_gather_ints(n_rows, dev)
+        row0, n_total = sum(counts[:comm.rank]), sum(counts)
+        if n_total >= 2 ** 31:
+            raise ValueError("sober_b200 supports fewer than 2^31 candidates")
+        if calc_obj is not None and comm.world > 1:
+            raise NotImplementedError("calc_obj with sharded candidates")
+
+        if init_weights is None:
+            mu = torch.full((n_rows,), 1.0, dtype=torch.float64, device=dev) / n_total
+        else:
+            if init_weights.shape != (n_rows,):
+                raise ValueError("init_weights must have shape (len(pts_rec),)")
+            mu = ops.f64(init_weights)
+
+        spec = introspect(kernel) if o.fuse else None
+        if spec is not None and spec.d is not None and spec.d != X.shape[1]:
+            raise ValueError("lengthscale dimension does not match the inputs")
+        center = inv_ls = None
+        if spec is not None and spec.stationary:
+            center = Z.mean(0).contiguous()
+            inv_ls = ops.f64(spec.inv_ls).expand(X.shape[1]).contiguous()
+
+        U, Uext, table = self._nystrom(Z, num_pts - 1, kernel, spec, center, inv_ls)
+        n = U.shape[0]
+        S = 2 * (n + 1)
+        st = {"spec": spec, "table": table, "kernel": kernel, "X": X, "Z": Z,
+              "pts": self._points(X, spec, center, inv_ls) if spec is not None else None}
+        UextT = Uext.T.contiguous()
+
+        idx, mass, n_local = ops.compact_nonzero(mu)
+        live = comm.all_gather_ints(n_local, dev)
+        pos0, remaining = sum(live[:comm.rank]), sum(live)
+        obj = None if calc_obj is None else (-1 * calc_obj(pts_rec.to(dev))).to(torch.float64)
+
+        while True:
+            if remaining <= S:
+                sel_idx, sel_w = self._finish(st, idx, mass, n_local, pos0, remaining, n, UextT, row0, obj)
+                break
+            E = remaining // S
+            ES = E * S
+            at, totw = self._accumulate(st, idx, mass, n_local, pos0, ES, S)
+            Lp = at.shape[1]
+            t0 = min(max(ES - pos0, 0), n_local)           # first local offset belonging to the remainder
+            extra = torch.zeros(Lp + 3, dtype=torch.float64, device=dev)
+            if t0 < n_local:
+                # second count of the remainder into the last group (SOBER/_rchq.py:153-164)
+                tail_at, tail_tw = self._accumulate(st, idx[t0:], mass[t0:], n_local - t0, 0, n_local - t0, 1)
+                extra[:Lp] = tail_at[0]
+                extra[Lp] = tail_tw[0]
+            objs = None
+            if obj is not None:
+                objs = torch.zeros((S, 1), dtype=torch.float64, device=dev)
+                row = obj[idx.long()].reshape(1, -1).contiguous()
+                ops.group_accumulate_gram(row, mass, pos0, ES, S, objs, None)
+                if t0 < n_local:
+                    extra[Lp + 1] = torch.dot(row[0, t0:], mass[t0:])
+            if comm.world > 1:
+                packed = torch.cat([at.reshape(-1), totw, extra])
+                comm.all_reduce(packed)
+                at = packed[:S * Lp].reshape(S, Lp)
+                totw = packed[S * Lp:S * Lp + S]
+                extra = packed[S * Lp + S:]
+            at[S - 1] += extra[:Lp]
+            totw = totw.clone()
+            totw[S - 1] += extra[Lp]
+            bary = at @ UextT                                   # (S x n)  == (U @ X_for_nys).T
+            if objs is not None:
+                objs[S - 1, 0] += extra[Lp + 1]
+                bary = torch.cat([bary, objs], 1)
+            if self.trace is not None:
+                self.trace("group", {"At": at.clone(), "totw": totw.clone(), "Xt_unnormalised": bary.clone(),
+                                     "R": remaining, "E": E})
+            bary = bary / totw.unsqueeze(1)
+            wfull = _car.caratheodory(ops, bary, totw, o.nullspace, self.nullspace)
+            if obj is not None:
+                wfull = self._objective_step(bary[:, :n], bary[:, n], wfull)
+            kept = wfull > 0
+            rank = (torch.cumsum(kept.to(torch.int32), 0) - kept.to(torch.int32)).to(torch.int32)
+            keep = KeepMap(kept.tolist(), S, ES)              # the one host sync of the iteration
+            new_pos0 = keep.before(pos0)
+            new_local = keep.before(pos0 + n_local) - new_pos0
+            idx, mass = ops.update_compact(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, keep.K,
+                                           keep.tail_keep, new_pos0, new_local)
+            pos0, n_local, remaining = new_pos0, new_local, keep.before(remaining)
+
+        # in-place sparse result in the caller's weight vector (SOBER/_rchq.py:109-110, 203-218)
+        if init_weights is not None:
+            mine = (sel_idx >= row0) & (sel_idx < row0 + n_rows)
+            loc, w_loc = (sel_idx[mine] - row0).contiguous(), sel_w[mine].contiguous()
+            if mu.data_ptr() == init_weights.data_ptr():
+                ops.scatter_result(mu, loc, w_loc)
+            else:
+                init_weights.zero_()
+                init_weights[loc.to(init_weights.device)] = w_loc.to(init_weights.device, init_weights.dtype)
+            sel_w = sel_w.to(init_weights.dtype)
+        return sel_idx, sel_w
+
+    # -----------------------------------------------------------------------------------------------------
+    def _finish(self, st, idx, mass, n_local, pos0, remaining, n, UextT, row0, obj):
+        """The two terminal branches, SOBER/_rchq.py:72-75 (R <= n+1) and :77-114 (n+1 < R <= S)."""
+        ops, comm, o = self.ops, self.comm, self.opts
+        dev = ops.device
+        all_mass = torch.zeros(remaining, dtype=torch.float64, device=dev)
+        all_idx = torch.zeros(remaining, dtype=torch.int64, device=dev)
+        all_mass[pos0:pos0 + n_local] = mass
+        all_idx[pos0:pos0 + n_local] = idx.long() + row0
+        if remaining <= n + 1:
+            if comm.world > 1:
+                comm.all_reduce(all_mass)
+                comm.all_reduce(all_idx)
+            live = all_mass > 0
+            return all_idx[live], all_mass[live]
+        if remaining > 0 and n_local > 0:
+            feats_t, _ = self._accumulate(st, idx, None, n_local, pos0, 0, remaining)     # (R x L'), unit weights
+        else:
+            Lp = UextT.shape[0]
+            feats_t = torch.zeros((remaining, Lp), dtype=torch.float64, device=dev)
+        if comm.world > 1:
+            comm.all_reduce(feats_t)
+            comm.all_reduce(all_mass)
+            comm.all_reduce(all_idx)
+        feats = feats_t @ UextT                                                            # (R x n)
+        if obj is not None:
+            alive_obj = obj[all_idx]
+            feats = torch.cat([feats, alive_obj.unsqueeze(1)], 1)
+        wfull = _car.caratheodory(ops, feats, all_mass, o.nullspace, self.nullspace)
+        if obj is not None:
+            # NB the reference indexes ``obj`` with POSITIONS here (SOBER/_rchq.py:89), kept as is
+            live = torch.nonzero(wfull > 0).reshape(-1)
+            wfull = self._objective_step(feats[:, :n], None, wfull, obj_vals=obj[live])
+        live = wfull > 0
+        return all_idx[live], wfull[live]
+
+    def _objective_step(self, feats, obj_col, wfull, obj_vals=None):
+        """One extra null-space move on the n+2 survivors, signed to increase the objective
+        (SOBER/_rchq.py:87-106 and :177-196).  Tiny: runs as torch ops on the device."""
+        live = torch.nonzero(wfull > 0).reshape(-1)
+        w = wfull[live]
+        pts = torch.cat([feats[live].T, torch.ones((1, len(live)), dtype=feats.dtype, device=feats.device)], 0)
+        _, _, vh = torch.linalg.svd(pts)
+        direction = vh[-1]
+        vals = obj_col[live] if obj_vals is None else obj_vals
+        if torch.dot(vals, direction) < 0:
+            direction = -direction
+        pos = direction > 0
+        ratio = torch.zeros_like(w)
+        ratio[pos] = w[pos] / direction[pos]
+        cand = torch.arange(len(w), device=w.device)[pos]
+        pivot = cand[torch.argmin(ratio[pos])]
+        w = w - ratio[pivot] * direction
+        w[pivot] = 0.0
+        out = torch.zeros_like(wfull)
+        out[live] = torch.where(w > 0, w, torch.zeros_like(w))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# public entry point
+# ---------------------------------------------------------------------------------------------------------
+_default_ops = None
+_default_comm = None
+
+
+def _ops():
+    global _default_ops
+    if _default_ops is None:
+        from ._ops import CudaOps
+        _default_ops = CudaOps()
+    _default_ops.variant = options.k1_variant
+    return _default_ops
+
+
+def set_communicator(comm):
+    """``None`` -> single process; a ``Sharded`` instance -> row-sharded candidates."""
+    global _default_comm
+    _default_comm = comm
+
+
+def recombination(
+    pts_rec,            # candidates (N, d); with a communicator set: this rank's contiguous row shard
+    pts_nys,            # Nystrom landmarks (L, d), replicated
+    num_pts,            # batch size b: at most b points are returned
+    kernel,             # SOBER Kernel object or any callable kernel(x, y) -> Gram
+    device,             # ignored, as in the reference (SOBER/_rchq.py:30): the CUDA device is used
+    dtype,              # ignored, as in the reference: float64 arithmetic
+    init_weights=None,  # (N,) importance weights; MUTATED IN PLACE into the sparse solution
+    calc_obj=None,      # optional objective callable (SOBER/_rchq.py:67-69)
+):
+    """Same contract as ``SOBER._rchq.recombination`` (SOBER/_rchq.py:5-31): returns ``(idx, w)`` with ``idx`` the
+    ascending int64 indices of at most ``num_pts`` selected candidates and ``w > 0`` their weights
+    (``w.sum() == init_weights.sum()``), both on the CUDA device."""
+    return Recombiner(_ops(), _default_comm).run(pts_rec, pts_nys, num_pts, kernel, init_weights, calc_obj)

@@ -1,0 +1,62 @@
+"""Process-wide options of the B200 path.
+
+The reference's own knobs are the global device/dtype of ``SOBER/_settings.py:3-22`` (which ``recombination``
+obeys instead of its ``device`` / ``dtype`` arguments, ``SOBER/_rchq.py:30``).  Here the device is always the
+current CUDA device and the arithmetic is float64; the extra knobs select how closely the N-independent
+L x L / S x S steps imitate the reference:
+
+``mode="parity"``  Nystrom Gram from the kernel callable itself, the reference's PSD gate (Cholesky AND bitwise
+                   symmetry AND non-symmetric ``eig``; ``SOBER/_utils.py:117-157``), ``torch.svd_lowrank`` and the
+                   null space from the full ``torch.linalg.svd`` (``SOBER/_rchq.py:231-234``) -- i.e. exactly the
+                   reference's op sequence on this device.  Slow (``eig``) but index-identical to the reference
+                   run on the same device.
+``mode="fast"``    Gram from the CUDA kernel (symmetric), the gate reduced to what it does in practice for an
+                   (always bitwise-asymmetric) gpytorch Gram -- ``sqrt(K*K^T)`` then Cholesky with escalating
+                   jitter -- and a Householder-QR null space.  Same algorithm, different (equally valid) null-space
+                   basis: weights/moments invariants hold, indices are those of the oracle run with the same basis.
+
+Every knob can be set individually; ``SOBER_B200_MODE`` picks the preset at import.
+"""
+import contextlib
+import os
+
+_PRESETS = {
+    "parity": dict(gram="callable", gate="reference", nullspace="svd"),
+    "fast": dict(gram="cuda", gate="cholesky", nullspace="qr"),
+}
+
+
+class Options:
+    def __init__(self, mode=None):
+        self.set_mode(mode or os.environ.get("SOBER_B200_MODE", "fast"))
+        self.fuse = True              # introspect Kernel objects; False forces the generic-callable path
+        self.generic_chunk = 1 << 16  # candidates per Gram tile on the generic path
+        self.k1_variant = 0           # 0 auto, 1 tiled, 2 small-d register kernel
+        self.stats = None             # optional dict that receives per-stage timings (forces syncs)
+
+    def set_mode(self, mode):
+        if mode not in _PRESETS:
+            raise ValueError("mode must be one of %s" % sorted(_PRESETS))
+        self.mode = mode
+        for k, v in _PRESETS[mode].items():
+            setattr(self, k, v)
+
+
+options = Options()
+
+
+@contextlib.contextmanager
+def configure(**kw):
+    """Temporarily override options: ``with configure(mode="parity"): ...``"""
+    saved = dict(options.__dict__)
+    try:
+        if "mode" in kw:
+            options.set_mode(kw.pop("mode"))
+        for k, v in kw.items():
+            if k not in saved:
+                raise AttributeError(k)
+            setattr(options, k, v)
+        yield options
+    finally:
+        options.__dict__.clear()
+        options.__dict__.update(saved)

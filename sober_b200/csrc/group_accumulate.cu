@@ -1,0 +1,417 @@
+// K1 -- fused cross-kernel + weighted strided group sums.
+//
+// Replaces SOBER/_rchq.py:116-136,152 (and :35 / :78 when used as a plain Gram): the reference materialises
+// K = kernel(pt_nys, samp[idx]) as an (E, L, S) tensor, multiplies by mu and sums over E.  Here every
+// candidate is streamed once per pass, its L kernel values are formed in registers and folded straight into
+// the (S x L) accumulator; nothing of size N x L ever exists.
+//
+// Two kernels share one contract:
+//   * group_small  : d <= 8.  Landmarks live in registers (one lane = TL landmarks), the warp walks the rows
+//                    of its TG groups, candidate records are warp-uniform (broadcast) loads.  FP64-pipe bound.
+//   * group_tiled  : any d.  64 landmarks x 64 groups per CTA, the <x, z> contraction runs over d in chunks of
+//                    16 staged through shared memory, 4x4 register tile per thread.
+// Rows are split across gridDim.z; partial sums go to a workspace and are reduced in a fixed order
+// (deterministic: no atomics), which also applies the output scale.
+#include "common.cuh"
+
+namespace sober {
+
+struct GroupParams {
+    const double* X;
+    int64_t ldx;
+    const double* xn;
+    int64_t xn_stride;
+    const int32_t* idx;
+    const double* mu;
+    int64_t n_local, pos0, ES;
+    int S, L, d;
+    const double* Zt;
+    const double* zn;
+    double* out;       // [nsplit][S][L]  (or At itself when nsplit == 1)
+    double* totw_out;  // [nsplit][S]
+    int64_t row_begin, row_end, rows_per_split;
+    double scale;      // applied at store time when nsplit == 1, else by the reduce kernel
+};
+
+// -------------------------------------------------------------------------------------------------
+// small-d register kernel
+// -------------------------------------------------------------------------------------------------
+template <int D, int FAM, int TL, int TG>
+__global__ void __launch_bounds__(128) group_small_kernel(const GroupParams p) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int g0 = blockIdx.x * TG;
+    const int l0 = (blockIdx.y * 4 + warp) * (32 * TL);
+    if (l0 >= p.L) return;  // whole warp out of range (no block-level sync in this kernel)
+
+    double zt[TL][D], zn[TL];
+#pragma unroll
+    for (int i = 0; i < TL; ++i) {
+        const int l = l0 + lane + 32 * i;
+        const bool ok = l < p.L;
+#pragma unroll
+        for (int k = 0; k < D; ++k) zt[i][k] = ok ? __ldg(p.Zt + (int64_t)l * D + k) : 0.0;
+        zn[i] = ok ? __ldg(p.zn + l) : 0.0;
+    }
+
+    double acc[TL][TG];
+    double tw[TG];
+#pragma unroll
+    for (int j = 0; j < TG; ++j) {
+        tw[j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < TL; ++i) acc[i][j] = 0.0;
+    }
+
+    const int64_t r0 = p.row_begin + (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t r1 = min(p.row_end, r0 + p.rows_per_split);
+    const int64_t hi = p.pos0 + p.n_local;
+
+    for (int64_t e = r0; e < r1; ++e) {
+        double x[TG][D], xn[TG], w[TG];
+#pragma unroll
+        for (int j = 0; j < TG; ++j) {
+            const int g = g0 + j;
+            const int64_t pos = e * p.S + g;
+            const bool ok = (g < p.S) && (pos >= p.pos0) && (pos < hi);
+            const int64_t loc = pos - p.pos0;
+            int64_t row = 0;
+            w[j] = 0.0;
+            if (ok) {
+                row = p.idx ? (int64_t)__ldg(p.idx + loc) : loc;
+                w[j] = p.mu ? __ldg(p.mu + loc) : 1.0;
+            }
+            const double* xr = p.X + row * p.ldx;
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[j][k] = ok ? __ldg(xr + k) : 0.0;
+            xn[j] = ok ? __ldg(p.xn + row * p.xn_stride) : 0.0;
+            if (pos < p.ES) tw[j] += w[j];
+        }
+#pragma unroll
+        for (int j = 0; j < TG; ++j) {
+#pragma unroll
+            for (int i = 0; i < TL; ++i) {
+                double dot = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) dot = fma(x[j][k], zt[i][k], dot);
+                const double kv = kernel_value<FAM>(dot, xn[j], zn[i]);
+                acc[i][j] = fma(kv, w[j], acc[i][j]);
+            }
+        }
+    }
+
+    double* out = p.out + (int64_t)blockIdx.z * p.S * p.L;
+#pragma unroll
+    for (int j = 0; j < TG; ++j) {
+        const int g = g0 + j;
+        if (g >= p.S) continue;
+#pragma unroll
+        for (int i = 0; i < TL; ++i) {
+            const int l = l0 + lane + 32 * i;
+            if (l < p.L) out[(int64_t)g * p.L + l] = acc[i][j] * p.scale;
+        }
+        if (blockIdx.y == 0 && warp == 0 && lane == 0) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw[j];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// generic tiled kernel
+// -------------------------------------------------------------------------------------------------
+constexpr int TM = 64;   // landmarks per CTA
+constexpr int TN = 64;   // groups per CTA
+constexpr int KC = 16;   // contraction chunk
+constexpr int LDS_ROW = 65;
+
+template <int FAM>
+__global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
+    __shared__ double Zs[KC][LDS_ROW];
+    __shared__ double Xs[KC][LDS_ROW];
+    __shared__ double s_w[TN], s_xn[TN];
+    __shared__ int64_t s_row[TN];
+
+    const int t = threadIdx.x;
+    const int tx = t & 15, ty = t >> 4;
+    const int g0 = blockIdx.x * TN;
+    const int l0 = blockIdx.y * TM;
+
+    double zn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int l = l0 + ty + 16 * i;
+        zn[i] = l < p.L ? __ldg(p.zn + l) : 0.0;
+    }
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    double tw = 0.0;
+
+    const int64_t r0 = p.row_begin + (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t r1 = min(p.row_end, r0 + p.rows_per_split);
+    const int64_t hi = p.pos0 + p.n_local;
+    const int kk_ld = t & 15;   // contraction index this thread loads
+    const int c_ld = t >> 4;    // first of 4 tile columns this thread loads (c_ld + 16 * pass)
+
+    for (int64_t e = r0; e < r1; ++e) {
+        if (t < TN) {
+            const int g = g0 + t;
+            const int64_t pos = e * p.S + g;
+            const bool ok = (g < p.S) && (pos >= p.pos0) && (pos < hi);
+            int64_t row = -1;
+            double w = 0.0, xn = 0.0;
+            if (ok) {
+                const int64_t loc = pos - p.pos0;
+                row = p.idx ? (int64_t)__ldg(p.idx + loc) : loc;
+                w = p.mu ? __ldg(p.mu + loc) : 1.0;
+                xn = __ldg(p.xn + row * p.xn_stride);
+                if (pos < p.ES) tw += w;
+            }
+            s_row[t] = row;
+            s_w[t] = w;
+            s_xn[t] = xn;
+        }
+        __syncthreads();
+
+        double dot[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dot[i][j] = 0.0;
+
+        for (int k0 = 0; k0 < p.d; k0 += KC) {
+            const int k = k0 + kk_ld;
+            const bool kok = k < p.d;
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+                const int c = c_ld + 16 * pass;
+                const int l = l0 + c;
+                Zs[kk_ld][c] = (kok && l < p.L) ? __ldg(p.Zt + (int64_t)l * p.d + k) : 0.0;
+                const int64_t row = s_row[c];
+                Xs[kk_ld][c] = (kok && row >= 0) ? __ldg(p.X + row * p.ldx + k) : 0.0;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < KC; ++kk) {
+                double z[4], x[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) z[i] = Zs[kk][ty + 16 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = Xs[kk][tx + 16 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dot[i][j] = fma(z[i], x[j], dot[i][j]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double w = s_w[tx + 16 * j];
+            const double xn = s_xn[tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double kv = kernel_value<FAM>(dot[i][j], xn, zn[i]);
+                acc[i][j] = fma(kv, w, acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+
+    double* out = p.out + (int64_t)blockIdx.z * p.S * p.L;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int g = g0 + tx + 16 * j;
+        if (g >= p.S) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int l = l0 + ty + 16 * i;
+            if (l < p.L) out[(int64_t)g * p.L + l] = acc[i][j] * p.scale;
+        }
+    }
+    if (blockIdx.y == 0 && t < TN && g0 + t < p.S) p.totw_out[(int64_t)blockIdx.z * p.S + g0 + t] = tw;
+}
+
+// fixed-order reduction of the row-splits; applies the output scale
+__global__ void reduce_splits_kernel(const double* __restrict__ part, const double* __restrict__ tw_part,
+                                     int nsplit, int64_t SL, int S, double scale, double* __restrict__ At,
+                                     double* __restrict__ totw) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < SL) {
+        double s = 0.0;
+        for (int z = 0; z < nsplit; ++z) s += part[(int64_t)z * SL + i];
+        At[i] = s * scale;
+    }
+    if (i < S) {
+        double s = 0.0;
+        for (int z = 0; z < nsplit; ++z) s += tw_part[(int64_t)z * S + i];
+        totw[i] = s;
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// reduction of a Gram tile produced by an opaque callable
+// -------------------------------------------------------------------------------------------------
+__global__ void group_gram_kernel(const double* __restrict__ G, int64_t ldg, int L, int64_t m,
+                                  const double* __restrict__ mu, int64_t pos_begin, int64_t ES, int S,
+                                  double* __restrict__ At, double* __restrict__ totw) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y * blockDim.y + threadIdx.y;
+    if (g >= S || l >= L) return;
+    // first j with (pos_begin + j) mod S == g
+    int64_t j = (g - (pos_begin % S) + S) % S;
+    double s = 0.0, tw = 0.0;
+    for (; j < m; j += S) {
+        const double w = mu ? mu[j] : 1.0;
+        s = fma(G[(int64_t)l * ldg + j], w, s);
+        if (pos_begin + j < ES) tw += w;
+    }
+    At[(int64_t)g * L + l] += s;
+    if (l == 0 && totw) totw[g] += tw;
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+struct Plan {
+    bool small;
+    int tl, tg;
+    dim3 grid, block;
+    int nsplit;
+    int64_t rows_per_split, row_begin, row_end;
+};
+
+static bool plan_group(const sober_group_args* a, Plan* pl) {
+    if (!a || a->S <= 0 || a->L <= 0 || a->d <= 0 || a->n_local < 0) return false;
+    const int64_t hi = a->pos0 + a->n_local;
+    pl->row_begin = a->pos0 / a->S;
+    pl->row_end = a->n_local > 0 ? ceil_div(hi, a->S) : pl->row_begin;
+    const int64_t rows = pl->row_end - pl->row_begin;
+    pl->small = (a->variant == 2) || (a->variant == 0 && a->d <= 8);
+    if (a->variant == 2 && a->d > 8) return false;
+    int64_t gx, gy;
+    if (pl->small) {
+        pl->tl = 2;
+        pl->tg = 4;
+        gx = ceil_div(a->S, pl->tg);
+        gy = ceil_div(a->L, 4 * 32 * pl->tl);
+        pl->block = dim3(128);
+    } else {
+        gx = ceil_div(a->S, TN);
+        gy = ceil_div(a->L, TM);
+        pl->block = dim3(256);
+    }
+    const int64_t target = (int64_t)sm_count() * (pl->small ? 16 : 8);
+    int64_t ns = ceil_div(target, gx * gy);
+    if (ns > rows) ns = rows;
+    if (ns < 1) ns = 1;
+    if (ns > 65535) ns = 65535;
+    pl->rows_per_split = rows > 0 ? ceil_div(rows, ns) : 1;
+    pl->nsplit = rows > 0 ? (int)ceil_div(rows, pl->rows_per_split) : 1;
+    pl->grid = dim3((unsigned)gx, (unsigned)gy, (unsigned)pl->nsplit);
+    return gy <= 65535;
+}
+
+template <int D, int FAM>
+static void launch_small(const Plan& pl, const GroupParams& p, cudaStream_t st) {
+    group_small_kernel<D, FAM, 2, 4><<<pl.grid, pl.block, 0, st>>>(p);
+}
+
+template <int FAM>
+static bool launch_small_d(const Plan& pl, const GroupParams& p, cudaStream_t st) {
+    switch (p.d) {
+        case 1: launch_small<1, FAM>(pl, p, st); return true;
+        case 2: launch_small<2, FAM>(pl, p, st); return true;
+        case 3: launch_small<3, FAM>(pl, p, st); return true;
+        case 4: launch_small<4, FAM>(pl, p, st); return true;
+        case 5: launch_small<5, FAM>(pl, p, st); return true;
+        case 6: launch_small<6, FAM>(pl, p, st); return true;
+        case 7: launch_small<7, FAM>(pl, p, st); return true;
+        case 8: launch_small<8, FAM>(pl, p, st); return true;
+        default: return false;
+    }
+}
+
+template <int FAM>
+static bool launch_family(const Plan& pl, const GroupParams& p, cudaStream_t st) {
+    if (pl.small) return launch_small_d<FAM>(pl, p, st);
+    group_tiled_kernel<FAM><<<pl.grid, pl.block, 0, st>>>(p);
+    return true;
+}
+
+}  // namespace sober
+
+using namespace sober;
+
+extern "C" int64_t sober_group_accumulate_workspace(const sober_group_args* a) {
+    Plan pl;
+    if (!plan_group(a, &pl)) return -1;
+    if (pl.nsplit <= 1) return 8 * (int64_t)a->S;  // totw staging only
+    return (int64_t)pl.nsplit * ((int64_t)a->S * a->L + a->S) * 8;
+}
+
+extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace, int64_t workspace_bytes,
+                                      void* stream) {
+    Plan pl;
+    if (!plan_group(a, &pl)) return SOBER_ERR_ARG;
+    if (!a->X || !a->xn || !a->Zt || !a->zn || !a->At || !a->totw) return SOBER_ERR_ARG;
+    if (a->family < SOBER_RBF || a->family > SOBER_TANIMOTO) return SOBER_ERR_UNSUPPORTED;
+    const int64_t need = sober_group_accumulate_workspace(a);
+    if (need > workspace_bytes || (need > 0 && !workspace)) return SOBER_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t SL = (int64_t)a->S * a->L;
+
+    if (pl.row_end <= pl.row_begin) {  // nothing owned: zero contribution
+        SOBER_CUDA_CHECK(cudaMemsetAsync(a->At, 0, SL * 8, st));
+        SOBER_CUDA_CHECK(cudaMemsetAsync(a->totw, 0, (int64_t)a->S * 8, st));
+        return SOBER_OK;
+    }
+
+    GroupParams p;
+    p.X = a->X; p.ldx = a->ldx; p.xn = a->xn; p.xn_stride = a->xn_stride;
+    p.idx = a->idx; p.mu = a->mu;
+    p.n_local = a->n_local; p.pos0 = a->pos0; p.ES = a->ES;
+    p.S = a->S; p.L = a->L; p.d = a->d;
+    p.Zt = a->Zt; p.zn = a->zn;
+    p.row_begin = pl.row_begin; p.row_end = pl.row_end; p.rows_per_split = pl.rows_per_split;
+    double* ws = (double*)workspace;
+    if (pl.nsplit == 1) {
+        p.out = a->At;
+        p.totw_out = a->totw;
+        p.scale = a->outputscale;
+    } else {
+        p.out = ws;
+        p.totw_out = ws + (int64_t)pl.nsplit * SL;
+        p.scale = 1.0;
+    }
+    bool ok = false;
+    switch (a->family) {
+        case SOBER_RBF: ok = launch_family<SOBER_RBF>(pl, p, st); break;
+        case SOBER_MATERN12: ok = launch_family<SOBER_MATERN12>(pl, p, st); break;
+        case SOBER_MATERN32: ok = launch_family<SOBER_MATERN32>(pl, p, st); break;
+        case SOBER_MATERN52: ok = launch_family<SOBER_MATERN52>(pl, p, st); break;
+        case SOBER_TANIMOTO: ok = launch_family<SOBER_TANIMOTO>(pl, p, st); break;
+    }
+    if (!ok) return SOBER_ERR_UNSUPPORTED;
+    SOBER_LAUNCH_CHECK("group_accumulate");
+    if (pl.nsplit > 1) {
+        const int64_t n = SL > a->S ? SL : a->S;
+        reduce_splits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, ws + (int64_t)pl.nsplit * SL, pl.nsplit,
+                                                                        SL, a->S, a->outputscale, a->At, a->totw);
+        SOBER_LAUNCH_CHECK("reduce_splits");
+    }
+    return SOBER_OK;
+}
+
+extern "C" int sober_group_accumulate_gram(const double* G, int64_t ldg, int32_t L, int64_t m, const double* mu,
+                                           int64_t pos_begin, int64_t ES, int32_t S, double* At, double* totw,
+                                           void* stream) {
+    if (!G || !At || L <= 0 || S <= 0 || m < 0 || ldg < m) return SOBER_ERR_ARG;
+    if (m == 0) return SOBER_OK;
+    dim3 block(32, 8);
+    dim3 grid((unsigned)ceil_div(S, 32), (unsigned)ceil_div(L, 8));
+    if (grid.y > 65535) return SOBER_ERR_UNSUPPORTED;
+    group_gram_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(G, ldg, L, m, mu, pos_begin, ES, S, At, totw);
+    SOBER_LAUNCH_CHECK("group_gram");
+    return SOBER_OK;
+}

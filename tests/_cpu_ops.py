@@ -1,0 +1,106 @@
+"""TEST DOUBLE for ``sober_b200._ops.CudaOps``: the same interface computed with plain torch on the CPU.
+
+Lives under tests/ on purpose -- the product has no CPU path.  It lets the CPU suite exercise the HOST logic of
+``sober_b200._rchq.Recombiner`` (grouping, remainder handling, closed-form compaction, sharding over gloo)
+against the oracle / golden fixtures without a GPU.  The arithmetic mirrors the CUDA kernels' formulas
+(expanded distance on prepared points), not the oracle's, so it also cross-checks the data layouts.
+"""
+import math
+
+import torch
+
+from oracle import rchq as oracle
+from sober_b200._ops import LandmarkTable, PointSet  # plain containers, no CUDA needed
+
+RBF, MATERN12, MATERN32, MATERN52, TANIMOTO = range(5)
+
+
+def kernel_values(dot, xn, zn, family):
+    """dot: (m, L) = x . zt ; xn: (m, 1) ; zn: (1, L)"""
+    if family == TANIMOTO:
+        return ((dot + 1e-6) / (1e-6 + xn + zn - dot)).clamp_min(0)
+    d2 = (xn + zn + dot).clamp_min(0)
+    if family == RBF:
+        return torch.exp(-0.5 * d2)
+    r = d2.clamp_min(1e-30).sqrt()
+    if family == MATERN12:
+        return torch.exp(-r)
+    if family == MATERN32:
+        s = math.sqrt(3.0) * r
+        return (1 + s) * torch.exp(-s)
+    s = math.sqrt(5.0) * r
+    return (1 + s + (5.0 / 3.0) * r * r) * torch.exp(-s)
+
+
+class TorchOps:
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.variant = 0
+
+    def f64(self, t):
+        return t.to(device=self.device, dtype=torch.float64).contiguous()
+
+    def prepare_points(self, X, center, inv_ls):
+        n, d = X.shape
+        ldp = (d + 2) // 2 * 2
+        P = torch.zeros((n, ldp), dtype=torch.float64)
+        P[:, :d] = (X - center) * inv_ls
+        P[:, d] = (P[:, :d] ** 2).sum(-1)
+        return PointSet(P, ldp, P[:, d], ldp, n, d)
+
+    def raw_points(self, X):
+        n, d = X.shape
+        return PointSet(X, X.stride(0), (X * X).sum(-1), 1, n, d)
+
+    def compact_nonzero(self, mu):
+        idx = torch.nonzero(mu != 0).reshape(-1).to(torch.int32)
+        return idx, mu[idx.long()].clone(), int(idx.numel())
+
+    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None):
+        L, d = lm.L, lm.d
+        at = torch.zeros((S, L), dtype=torch.float64)
+        totw = torch.zeros(S, dtype=torch.float64)
+        if n_local == 0:
+            return at, totw
+        rows = torch.arange(n_local) if idx is None else idx[:n_local].long()
+        w = torch.ones(n_local, dtype=torch.float64) if mu is None else mu[:n_local]
+        x = pts.rows[rows, :d]
+        xn = pts.xn[rows].reshape(-1, 1)
+        kv = kernel_values(x @ lm.zt.T, xn, lm.zn.reshape(1, -1), lm.family) * w.reshape(-1, 1)
+        pos = pos0 + torch.arange(n_local)
+        at.index_add_(0, pos % S, kv)
+        inside = pos < ES
+        totw.index_add_(0, (pos % S)[inside], w[inside])
+        return at * lm.outputscale, totw
+
+    def group_accumulate_gram(self, G, mu, pos_begin, ES, S, At, totw):
+        m = G.shape[1]
+        w = torch.ones(m, dtype=torch.float64) if mu is None else mu
+        pos = pos_begin + torch.arange(m)
+        At.index_add_(0, pos % S, (G * w.reshape(1, -1)).T.contiguous())
+        if totw is not None:
+            inside = pos < ES
+            totw.index_add_(0, (pos % S)[inside], w[inside])
+
+    def car_eliminate(self, basis_rows, mass, want_pivots=False):
+        removed = oracle.eliminate(basis_rows.T.clone(), mass, oracle.Factory())
+        if want_pivots:
+            k = basis_rows.shape[0]
+            piv = torch.full((max(k, 1),), -1, dtype=torch.int32)
+            piv[:len(removed)] = torch.tensor(removed, dtype=torch.int32)
+            return piv, torch.tensor([len(removed)], dtype=torch.int32)
+
+    def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out):
+        pos = pos0 + torch.arange(n_local)
+        g = torch.where(pos < ES, pos % S, torch.full_like(pos, S - 1))
+        keep = torch.where(pos < ES, wstar[g] > 0, torch.full_like(pos, bool(tail_keep), dtype=torch.bool))
+        dst = torch.where(pos < ES, (pos // S) * K + rank[g].long(), (ES // S) * K + (pos - ES)) - new_pos0
+        idx_out = torch.zeros(n_out, dtype=torch.int32)
+        mu_out = torch.zeros(n_out, dtype=torch.float64)
+        idx_out[dst[keep]] = idx[:n_local][keep]
+        mu_out[dst[keep]] = (mu[:n_local][keep] * wstar[g[keep]]) / totw[g[keep]]
+        return idx_out, mu_out
+
+    def scatter_result(self, dst, idx, w):
+        dst.zero_()
+        dst[idx] = w
