@@ -43,6 +43,8 @@ class CudaOps:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.variant = 0
         self._ws = None
+        self.launches = 0      # kernels launched through the C ABI (bench.py reports it)
+        self.timing = None     # None, or {name: [(start_event, end_event, work), ...]} filled per call
 
     # -- helpers -------------------------------------------------------------------------------------
     def _stream(self):
@@ -56,6 +58,27 @@ class CudaOps:
     def f64(self, t):
         return t.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
 
+    def _begin(self, name):
+        if self.timing is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    def _end(self, name, start, work):
+        if start is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self.timing.setdefault(name, []).append((start, ev, work))
+
+    def timing_summary(self):
+        """{name: (calls, total_ms, total_work)} -- call after a synchronize."""
+        out = {}
+        for name, recs in (self.timing or {}).items():
+            out[name] = (len(recs), sum(a.elapsed_time(b) for a, b, _ in recs), sum(w for _, _, w in recs))
+        return out
+
     # -- streaming passes ------------------------------------------------------------------------------
     def prepare_points(self, X, center, inv_ls):
         """(X - c) * inv_ls with the squared norm appended: the candidate layout for stationary families."""
@@ -63,8 +86,11 @@ class CudaOps:
         ldp = (d + 1 + 1) // 2 * 2  # even row stride keeps rows 16-byte aligned
         P = torch.empty((n, ldp), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
+            t0 = self._begin("prepare_points")
             check(self.lib.sober_prepare_points(_ptr(X), X.stride(0), n, d, _ptr(center), _ptr(inv_ls), _ptr(P), ldp,
                                                 self._stream()), "prepare_points")
+            self._end("prepare_points", t0, 8 * n * (d + ldp))
+        self.launches += 1
         return PointSet(P, ldp, P[:, d], ldp, n, d)
 
     def raw_points(self, X):
@@ -73,6 +99,7 @@ class CudaOps:
         xn = torch.empty(n, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             check(self.lib.sober_row_sqnorm(_ptr(X), X.stride(0), n, d, _ptr(xn), self._stream()), "row_sqnorm")
+        self.launches += 1
         return PointSet(X, X.stride(0), xn, 1, n, d)
 
     def compact_nonzero(self, mu):
@@ -84,8 +111,11 @@ class CudaOps:
         nbytes = self.lib.sober_compact_workspace(n)
         ws = self._workspace(nbytes)
         with torch.cuda.device(self.device):
+            t0 = self._begin("compact_nonzero")
             check(self.lib.sober_compact_nonzero(_ptr(mu), n, _ptr(idx), _ptr(out), _ptr(cnt), _ptr(ws), ws.numel(),
                                                  self._stream()), "compact_nonzero")
+            self._end("compact_nonzero", t0, 8 * n * 2 + 12 * n)
+        self.launches += 3
         r = int(cnt.item())
         return idx[:r], out[:r], r
 
@@ -111,8 +141,11 @@ class CudaOps:
             raise _lib.SoberB200Error("sober_b200: group_accumulate: bad arguments")
         ws = self._workspace(nbytes)
         with torch.cuda.device(self.device):
+            t0 = self._begin("group_accumulate")
             check(self.lib.sober_group_accumulate(C.byref(a), _ptr(ws), ws.numel(), self._stream()),
                   "group_accumulate")
+            self._end("group_accumulate", t0, int(n_local) * int(lm.L))      # work = kernel evaluations (pairs)
+        self.launches += 2 if nbytes > 0 else 1
         return At, totw
 
     def group_accumulate_gram(self, G, mu, pos_begin, ES, S, At, totw):
@@ -121,6 +154,7 @@ class CudaOps:
             check(self.lib.sober_group_accumulate_gram(_ptr(G), G.stride(0), L, m, _ptr(mu), int(pos_begin), int(ES),
                                                        int(S), _ptr(At), _ptr(totw), self._stream()),
                   "group_accumulate_gram")
+        self.launches += 1
 
     # -- CAR -----------------------------------------------------------------------------------------------
     def car_eliminate(self, basis_rows, mass, want_pivots=False):
@@ -132,8 +166,11 @@ class CudaOps:
         nbytes = self.lib.sober_car_workspace(k)
         flags = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
+            t0 = self._begin("car_eliminate")
             check(self.lib.sober_car_eliminate(_ptr(basis_rows), k, S, _ptr(mass), _ptr(piv), _ptr(steps), _ptr(flags),
                                                flags.numel() * 4, self._stream()), "car_eliminate")
+            self._end("car_eliminate", t0, k)                                   # work = elimination steps
+        self.launches += 1
         return (piv, steps) if want_pivots else None
 
     # -- update + compaction ----------------------------------------------------------------------------------
@@ -141,16 +178,20 @@ class CudaOps:
         idx_out = torch.empty(n_out, dtype=torch.int32, device=self.device)
         mu_out = torch.empty(n_out, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
+            t0 = self._begin("update_compact")
             check(self.lib.sober_update_compact(_ptr(idx), _ptr(mu), int(n_local), int(pos0), int(ES), int(S),
                                                 _ptr(wstar), _ptr(totw), _ptr(rank), int(K), int(bool(tail_keep)),
                                                 int(new_pos0), _ptr(idx_out), _ptr(mu_out), self._stream()),
                   "update_compact")
+            self._end("update_compact", t0, 12 * int(n_local) + 12 * int(n_out))  # work = HBM bytes
+        self.launches += 1
         return idx_out, mu_out
 
     def scatter_result(self, dst, idx, w):
         with torch.cuda.device(self.device):
             check(self.lib.sober_scatter_result(_ptr(dst), dst.numel(), _ptr(idx), _ptr(w), idx.numel(),
                                                 self._stream()), "scatter_result")
+        self.launches += 1
 
     def fp64_probe(self, blocks, iters):
         sink = torch.zeros(1, dtype=torch.float64, device=self.device)

@@ -346,7 +346,7 @@ using namespace sober;
 extern "C" int64_t sober_group_accumulate_workspace(const sober_group_args* a) {
     Plan pl;
     if (!plan_group(a, &pl)) return -1;
-    if (pl.nsplit <= 1) return 8 * (int64_t)a->S;  // totw staging only
+    if (pl.nsplit <= 1) return 0;  // single split: the kernel writes At / totw directly
     return (int64_t)pl.nsplit * ((int64_t)a->S * a->L + a->S) * 8;
 }
 
