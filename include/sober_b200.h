@@ -56,6 +56,14 @@ int sober_sm_count(int* out);
 int sober_prepare_points(const double* X, int64_t ldx, int64_t n, int32_t d, const double* center,
                          const double* inv_ls, double* P, int64_t ldp, void* stream);
 
+/* Small-d record layout for the register kernel of K1 (d <= 8, stationary families): one row per ALIVE point,
+ * in alive-list order,   rec[j] = [ (X[idx[j]] - center) * inv_ls  (d) | its squared norm | mu[j] | zero pad ],
+ * row stride ldr = d + 2 rounded up to even (16-byte aligned rows: the kernel stages them with 1-D TMA bulk
+ * copies).  idx NULL = identity, mu NULL = 1.  Fuses the gather `samp[idx]`, the lengthscale division and the
+ * norm of gpytorch's distance (SOBER/_rchq.py:124 -> covar_module.forward). */
+int sober_make_records(const double* X, int64_t ldx, int32_t d, const double* center, const double* inv_ls,
+                       const int32_t* idx, const double* mu, int64_t m, double* rec, int64_t ldr, void* stream);
+
 /* out[i] = sum_k X[i,k]^2  (Tanimoto |x|^2, SOBER/_drug_modelling.py:21-22). */
 int sober_row_sqnorm(const double* X, int64_t ldx, int64_t n, int32_t d, double* out, void* stream);
 
@@ -78,13 +86,17 @@ int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_out, double*
  * SOBER/_rchq.py:128-136) are accumulated into At (column p - ES, "the quirk") but not into totw.
  * Never materialises the (E, L, S) Gram of SOBER/_rchq.py:124.
  *
- * X / ldx / xn / xn_stride: candidate rows and their squared norms (for stationary families the output of
- *   sober_prepare_points: xn = P + d, xn_stride = ldp; for Tanimoto the raw rows and sober_row_sqnorm).
- * idx: local alive-list (row ids into X), NULL = identity.   mu: weights aligned with idx, NULL = 1.
+ * Two candidate layouts:
+ *  - indexed (any d): X / ldx / xn / xn_stride = candidate rows and their squared norms (stationary families: the
+ *    output of sober_prepare_points, xn = P + d, xn_stride = ldp; Tanimoto: the raw rows and sober_row_sqnorm);
+ *    idx = local alive-list (row ids into X), NULL = identity; mu = weights aligned with idx, NULL = 1.
+ *  - records (d <= 8): rec / ldr from sober_make_records, already in alive-list order (X, xn, idx, mu unused).
+ * Stationary families expect coordinates pre-multiplied by the family constant (1/sqrt2 RBF, 1 Matern-1/2,
+ * sqrt3 Matern-3/2, sqrt5 Matern-5/2): fold it into inv_ls.
  * Zt (L x d): landmark table -- stationary: -2 (z - c) * inv_ls ; Tanimoto: z.   zn (L): |.|^2 of the same.
  * At: S x L (transposed on purpose: coalesced stores and it is the left operand of the projection).
  * workspace holds the per-split partial sums (deterministic two-stage reduction, no atomics).
- * variant: 0 = automatic, 1 = force the generic tiled kernel, 2 = force the small-d register kernel.
+ * variant: 0 = automatic (records -> register kernel, else tiled), 1 = force the generic tiled kernel.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct sober_group_args {
     const double* X;
@@ -107,7 +119,9 @@ typedef struct sober_group_args {
     double* At;
     double* totw;
     int32_t variant;
-    int32_t reserved;
+    int32_t unit_weights; /* record layout only: ignore the weight stored in the records (plain Gram) */
+    const double* rec;    /* record layout (sober_make_records), row j = local position j; NULL = indexed layout */
+    int64_t ldr;
 } sober_group_args;
 
 int64_t sober_group_accumulate_workspace(const sober_group_args* args);
@@ -143,10 +157,12 @@ int sober_car_eliminate(double* basis, int32_t k, int32_t S, double* mu, int32_t
  *     kept:    mu_out[q - new_pos0] = (mu_in[j] * wstar[g]) / totw[g]      (g = S-1 for the tail)
  *              idx_out[q - new_pos0] = idx_in[j]
  *   rank[g] = number of kept groups below g, K = number of kept groups (both computed by the caller).
+ *   rec_in / rec_out (may be NULL): the record rows move with their points, weight slot (column d + 1) updated.
  * ------------------------------------------------------------------------------------------------- */
 int sober_update_compact(const int32_t* idx_in, const double* mu_in, int64_t n_local, int64_t pos0, int64_t ES,
                          int32_t S, const double* wstar, const double* totw, const int32_t* rank, int32_t K,
-                         int32_t tail_keep, int64_t new_pos0, int32_t* idx_out, double* mu_out, void* stream);
+                         int32_t tail_keep, int64_t new_pos0, int32_t* idx_out, double* mu_out,
+                         const double* rec_in, double* rec_out, int64_t ldr, int32_t d, void* stream);
 
 /* dst[:] = 0 ; dst[idx[j]] = w[j]   -- the in-place sparse result of SOBER/_rchq.py:109-110. */
 int sober_scatter_result(double* dst, int64_t n, const int64_t* idx, const double* w, int64_t m, void* stream);

@@ -14,6 +14,9 @@ OK = 0
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "unsupported shape/family", 4: "workspace too small"}
 
 RBF, MATERN12, MATERN32, MATERN52, TANIMOTO = range(5)
+# constant folded into the lengthscale so that the kernels see  RBF = exp(-d2), Matern = f(r), r = sqrt(d2)
+FAMILY_SCALE = {RBF: 0.5 ** 0.5, MATERN12: 1.0, MATERN32: 3.0 ** 0.5, MATERN52: 5.0 ** 0.5, TANIMOTO: 1.0}
+RECORD_MAX_D = 8   # the register kernel of K1 (record layout) covers d <= 8
 
 
 class GroupArgs(C.Structure):
@@ -27,7 +30,8 @@ class GroupArgs(C.Structure):
         ("outputscale", C.c_double),
         ("Zt", C.c_void_p), ("zn", C.c_void_p),
         ("At", C.c_void_p), ("totw", C.c_void_p),
-        ("variant", C.c_int32), ("reserved", C.c_int32),
+        ("variant", C.c_int32), ("unit_weights", C.c_int32),
+        ("rec", C.c_void_p), ("ldr", C.c_int64),
     ]
 
 
@@ -39,6 +43,7 @@ PROTOTYPES = {
     "sober_last_cuda_error": (C.c_char_p, []),
     "sober_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "sober_prepare_points": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _I64, _P]),
+    "sober_make_records": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _I64, _P, _I64, _P]),
     "sober_row_sqnorm": (C.c_int, [_P, _I64, _I64, _I32, _P, _P]),
     "sober_compact_workspace": (_I64, [_I64]),
     "sober_compact_nonzero": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I64, _P]),
@@ -47,7 +52,8 @@ PROTOTYPES = {
     "sober_group_accumulate_gram": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _I64, _I32, _P, _P, _P]),
     "sober_car_workspace": (_I64, [_I32]),
     "sober_car_eliminate": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _I64, _P]),
-    "sober_update_compact": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _I32, _I32, _I64, _P, _P, _P]),
+    "sober_update_compact": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _I32, _I32, _I64, _P, _P,
+                                       _P, _P, _I64, _I32, _P]),
     "sober_scatter_result": (C.c_int, [_P, _I64, _P, _P, _I64, _P]),
     "sober_fp64_probe": (C.c_int, [_I32, _I64, _P, _P]),
 }

@@ -20,10 +20,18 @@ def _ptr(t):
 
 
 class PointSet:
-    """Candidate (or landmark-as-candidate) rows in the layout K1 reads: ``rows`` (n x ld), ``xn`` view."""
+    """Candidate (or landmark-as-candidate) rows in a layout K1 reads.
 
-    def __init__(self, rows, ld, xn, xn_stride, n, d):
+    indexed layout: ``rows`` (n x ld) + ``xn`` view, addressed through an alive-list of row ids;
+    record layout : ``rec`` (m x ldr) rows ``[coords | norm | weight | pad]`` already in alive-list order."""
+
+    def __init__(self, rows, ld, xn, xn_stride, n, d, rec=None, ldr=0):
         self.rows, self.ld, self.xn, self.xn_stride, self.n, self.d = rows, ld, xn, xn_stride, n, d
+        self.rec, self.ldr = rec, ldr
+
+
+def record_stride(d):
+    return (d + 3) // 2 * 2
 
 
 class LandmarkTable:
@@ -93,6 +101,20 @@ class CudaOps:
         self.launches += 1
         return PointSet(P, ldp, P[:, d], ldp, n, d)
 
+    def make_records(self, X, center, inv_ls, idx=None, mu=None):
+        """Gather + (x - c) * inv_ls + norm + weight into the record layout (one 16-byte aligned row per point)."""
+        d = X.shape[1]
+        m = X.shape[0] if idx is None else idx.numel()
+        ldr = record_stride(d)
+        rec = torch.empty((m, ldr), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            t0 = self._begin("make_records")
+            check(self.lib.sober_make_records(_ptr(X), X.stride(0), d, _ptr(center), _ptr(inv_ls), _ptr(idx), _ptr(mu),
+                                              m, _ptr(rec), ldr, self._stream()), "make_records")
+            self._end("make_records", t0, 8 * m * (d + 2 + ldr))
+        self.launches += 1
+        return PointSet(None, 0, None, 0, m, d, rec=rec, ldr=ldr)
+
     def raw_points(self, X):
         """Tanimoto layout: the rows as they are plus |x|^2."""
         n, d = X.shape
@@ -120,15 +142,20 @@ class CudaOps:
         return idx[:r], out[:r], r
 
     # -- K1 ------------------------------------------------------------------------------------------------
-    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None):
-        """At (S x L) and totw (S) for the positions [pos0, pos0 + n_local) this device owns."""
+    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None, rec=None, unit_weights=False):
+        """At (S x L) and totw (S) for the positions [pos0, pos0 + n_local) this device owns.  ``rec``: record rows of
+        exactly those positions (record layout); otherwise ``pts`` + ``idx`` + ``mu`` (indexed layout)."""
         At = torch.empty((S, lm.L), dtype=torch.float64, device=self.device)
         totw = torch.empty(S, dtype=torch.float64, device=self.device)
         a = GroupArgs()
-        a.X, a.ldx = pts.rows.data_ptr(), pts.ld
-        a.xn, a.xn_stride = pts.xn.data_ptr(), pts.xn_stride
-        a.idx = None if idx is None else idx.data_ptr()
-        a.mu = None if mu is None else mu.data_ptr()
+        if rec is not None:
+            a.rec, a.ldr = rec.data_ptr(), rec.stride(0)
+            a.unit_weights = int(bool(unit_weights))
+        else:
+            a.X, a.ldx = pts.rows.data_ptr(), pts.ld
+            a.xn, a.xn_stride = pts.xn.data_ptr(), pts.xn_stride
+            a.idx = None if idx is None else idx.data_ptr()
+            a.mu = None if mu is None else mu.data_ptr()
         a.n_local, a.pos0, a.ES = int(n_local), int(pos0), int(ES)
         a.n_global = int(pos0 + n_local if n_global is None else n_global)
         a.S, a.L, a.d, a.family = int(S), int(lm.L), int(lm.d), int(lm.family)
@@ -174,18 +201,22 @@ class CudaOps:
         return (piv, steps) if want_pivots else None
 
     # -- update + compaction ----------------------------------------------------------------------------------
-    def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out):
+    def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out,
+                       rec=None, d=0):
         idx_out = torch.empty(n_out, dtype=torch.int32, device=self.device)
         mu_out = torch.empty(n_out, dtype=torch.float64, device=self.device)
+        ldr = 0 if rec is None else rec.stride(0)
+        rec_out = None if rec is None else torch.empty((n_out, ldr), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             t0 = self._begin("update_compact")
             check(self.lib.sober_update_compact(_ptr(idx), _ptr(mu), int(n_local), int(pos0), int(ES), int(S),
                                                 _ptr(wstar), _ptr(totw), _ptr(rank), int(K), int(bool(tail_keep)),
-                                                int(new_pos0), _ptr(idx_out), _ptr(mu_out), self._stream()),
+                                                int(new_pos0), _ptr(idx_out), _ptr(mu_out), _ptr(rec), _ptr(rec_out),
+                                                int(ldr), int(d), self._stream()),
                   "update_compact")
-            self._end("update_compact", t0, 12 * int(n_local) + 12 * int(n_out))  # work = HBM bytes
+            self._end("update_compact", t0, (12 + 8 * ldr) * (int(n_local) + int(n_out)))  # work = HBM bytes
         self.launches += 1
-        return idx_out, mu_out
+        return idx_out, mu_out, rec_out
 
     def scatter_result(self, dst, idx, w):
         with torch.cuda.device(self.device):

@@ -19,7 +19,7 @@ and the only collective per iteration is one all-reduce of the (S x L') accumula
 """
 import torch
 
-from . import _car, _nystrom, _psd
+from . import _car, _lib, _nystrom, _psd
 from ._kernel_spec import introspect
 from ._ops import LandmarkTable
 from ._settings import options
@@ -78,6 +78,17 @@ class KeepMap:
         return self.E * self.K + ((p - self.ES) if self.tail_keep else 0)
 
 
+class Alive:
+    """This rank's part of the compact alive-list, in position order: row ids, weights and -- record layout --
+    the record rows K1 streams."""
+
+    def __init__(self, idx, mass, rec=None):
+        self.idx, self.mass, self.rec = idx, mass, rec
+
+    def tail(self, t0):
+        return Alive(self.idx[t0:], self.mass[t0:], None if self.rec is None else self.rec[t0:])
+
+
 class Recombiner:
     def __init__(self, ops, comm=None, opts=None, nullspace=None, basis=None, trace=None):
         self.ops = ops
@@ -97,13 +108,19 @@ class Recombiner:
             return LandmarkTable((-2.0 * v).contiguous(), (v * v).sum(-1).contiguous(), spec.family, spec.outputscale)
         return LandmarkTable(pts.contiguous(), (pts * pts).sum(-1).contiguous(), spec.family, spec.outputscale)
 
+    def _use_records(self, spec, d):
+        return spec is not None and d <= _lib.RECORD_MAX_D and self.opts.k1_variant != 1
+
     def _points(self, X, spec, center, inv_ls):
+        if self._use_records(spec, X.shape[1]):
+            return self.ops.make_records(X, center, inv_ls)
         return self.ops.prepare_points(X, center, inv_ls) if spec.stationary else self.ops.raw_points(X)
 
     def _gram_T(self, pointset, table):
         """k(table, points)^T as an (m x L) matrix: K1 with one row of m singleton groups and unit weights."""
         m = pointset.n
-        at, _ = self.ops.group_accumulate(pointset, table, None, None, m, 0, 0, m)
+        at, _ = self.ops.group_accumulate(pointset, table, None, None, m, 0, 0, m, rec=pointset.rec,
+                                          unit_weights=True)
         return at
 
     def _nystrom(self, Z, n_basis, kernel, spec, center, inv_ls):
@@ -141,9 +158,11 @@ class Recombiner:
     # -----------------------------------------------------------------------------------------------------
     # one K1 pass over the local alive-list (fused kernel or generic callable)
     # -----------------------------------------------------------------------------------------------------
-    def _accumulate(self, st, idx, mu, n_local, pos0, ES, S):
+    def _accumulate(self, st, alive, n_local, pos0, ES, S, unit=False):
+        idx, mu = alive.idx, (None if unit else alive.mass)
         if st["spec"] is not None:
-            return self.ops.group_accumulate(st["pts"], st["table"], idx, mu, n_local, pos0, ES, S)
+            return self.ops.group_accumulate(st["pts"], st["table"], idx, mu, n_local, pos0, ES, S, rec=alive.rec,
+                                             unit_weights=unit)
         L = st["Z"].shape[0]
         dev = self.ops.device
         at = torch.zeros((S, L), dtype=torch.float64, device=dev)
@@ -183,35 +202,43 @@ class Recombiner:
         if spec is not None and spec.d is not None and spec.d != X.shape[1]:
             raise ValueError("lengthscale dimension does not match the inputs")
         center = inv_ls = None
+        d = X.shape[1]
         if spec is not None and spec.stationary:
+            # the family constant rides on the lengthscale: the kernels see exp(-d2) / f(sqrt(d2))  (_lib.FAMILY_SCALE)
             center = Z.mean(0).contiguous()
-            inv_ls = ops.f64(spec.inv_ls).expand(X.shape[1]).contiguous()
+            inv_ls = (ops.f64(spec.inv_ls) * _lib.FAMILY_SCALE[spec.family]).expand(d).contiguous()
+        elif spec is not None:
+            center = torch.zeros(d, dtype=torch.float64, device=dev)
+            inv_ls = torch.ones(d, dtype=torch.float64, device=dev)
+        records = self._use_records(spec, d)
 
         U, Uext, table = self._nystrom(Z, num_pts - 1, kernel, spec, center, inv_ls)
         n = U.shape[0]
         S = 2 * (n + 1)
         st = {"spec": spec, "table": table, "kernel": kernel, "X": X, "Z": Z,
-              "pts": self._points(X, spec, center, inv_ls) if spec is not None else None}
+              "pts": self._points(X, spec, center, inv_ls) if (spec is not None and not records) else None}
         UextT = Uext.T.contiguous()
 
         idx, mass, n_local = ops.compact_nonzero(mu)
+        alive = Alive(idx, mass, ops.make_records(X, center, inv_ls, idx, mass).rec if records else None)
         live = comm.all_gather_ints(n_local, dev)
         pos0, remaining = sum(live[:comm.rank]), sum(live)
         obj = None if calc_obj is None else (-1 * calc_obj(pts_rec.to(dev))).to(torch.float64)
 
         while True:
             if remaining <= S:
-                sel_idx, sel_w = self._finish(st, idx, mass, n_local, pos0, remaining, n, UextT, row0, obj)
+                sel_idx, sel_w = self._finish(st, alive, n_local, pos0, remaining, n, UextT, row0, obj)
                 break
             E = remaining // S
             ES = E * S
-            at, totw = self._accumulate(st, idx, mass, n_local, pos0, ES, S)
+            idx, mass = alive.idx, alive.mass
+            at, totw = self._accumulate(st, alive, n_local, pos0, ES, S)
             Lp = at.shape[1]
             t0 = min(max(ES - pos0, 0), n_local)           # first local offset belonging to the remainder
             extra = torch.zeros(Lp + 3, dtype=torch.float64, device=dev)
             if t0 < n_local:
                 # second count of the remainder into the last group (SOBER/_rchq.py:153-164)
-                tail_at, tail_tw = self._accumulate(st, idx[t0:], mass[t0:], n_local - t0, 0, n_local - t0, 1)
+                tail_at, tail_tw = self._accumulate(st, alive.tail(t0), n_local - t0, 0, n_local - t0, 1)
                 extra[:Lp] = tail_at[0]
                 extra[Lp] = tail_tw[0]
             objs = None
@@ -246,8 +273,8 @@ class Recombiner:
             keep = KeepMap(kept.tolist(), S, ES)              # the one host sync of the iteration
             new_pos0 = keep.before(pos0)
             new_local = keep.before(pos0 + n_local) - new_pos0
-            idx, mass = ops.update_compact(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, keep.K,
-                                           keep.tail_keep, new_pos0, new_local)
+            alive = Alive(*ops.update_compact(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, keep.K,
+                                              keep.tail_keep, new_pos0, new_local, rec=alive.rec, d=d))
             pos0, n_local, remaining = new_pos0, new_local, keep.before(remaining)
 
         # in-place sparse result in the caller's weight vector (SOBER/_rchq.py:109-110, 203-218)
@@ -263,10 +290,11 @@ class Recombiner:
         return sel_idx, sel_w
 
     # -----------------------------------------------------------------------------------------------------
-    def _finish(self, st, idx, mass, n_local, pos0, remaining, n, UextT, row0, obj):
+    def _finish(self, st, alive, n_local, pos0, remaining, n, UextT, row0, obj):
         """The two terminal branches, SOBER/_rchq.py:72-75 (R <= n+1) and :77-114 (n+1 < R <= S)."""
         ops, comm, o = self.ops, self.comm, self.opts
         dev = ops.device
+        idx, mass = alive.idx, alive.mass
         all_mass = torch.zeros(remaining, dtype=torch.float64, device=dev)
         all_idx = torch.zeros(remaining, dtype=torch.int64, device=dev)
         all_mass[pos0:pos0 + n_local] = mass
@@ -278,7 +306,7 @@ class Recombiner:
             live = all_mass > 0
             return all_idx[live], all_mass[live]
         if remaining > 0 and n_local > 0:
-            feats_t, _ = self._accumulate(st, idx, None, n_local, pos0, 0, remaining)     # (R x L'), unit weights
+            feats_t, _ = self._accumulate(st, alive, n_local, pos0, 0, remaining, unit=True)   # (R x L'), unit weights
         else:
             Lp = UextT.shape[0]
             feats_t = torch.zeros((remaining, Lp), dtype=torch.float64, device=dev)

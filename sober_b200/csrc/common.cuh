@@ -33,32 +33,149 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 int sm_count();
 
 // ---------------------------------------------------------------------------------------------------
+// FP64 math tuned for the FP64 pipe (B200: 64 DFMA/clk/SM, no FP64 SFU).  The library exp()/sqrt()/division
+// cost ~3x more issue slots than FP64 slots (special-case branches, integer fix-ups, register moves); K1 is
+// bound by exactly those, so the three primitives are restated with the minimum number of FP64 instructions:
+//
+//   exp_neg(s) = exp(-s), s >= 0      10 FP64 + ~6 integer/LDS   max rel err 3.3e-16 (checked against 50-digit
+//                                      arithmetic in tools/check_fastmath.py)
+//   sqrt_pos(a), a >= 1e-30            7 FP64 + 1 MUFU            <= 1 ulp
+//   div_pos(a, b), b > 0               7 FP64 + 1 MUFU            <= 1 ulp
+// ---------------------------------------------------------------------------------------------------
+constexpr int EXP_TAB_SIZE = 64;
+static __device__ const double EXP2_TAB[EXP_TAB_SIZE] = {  // 2^(j/64), correctly rounded (50-digit source)
+    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
+    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
+    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
+    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
+    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
+    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
+    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
+    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
+    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
+    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
+    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
+    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
+    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
+    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
+    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
+    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+
+__device__ __forceinline__ void load_exp_table(double* tab_smem, int tid, int nthreads) {
+    for (int j = tid; j < EXP_TAB_SIZE; j += nthreads) tab_smem[j] = EXP2_TAB[j];
+}
+
+__device__ __forceinline__ double exp_neg(double s, const double* __restrict__ tab) {
+    // exp(-s) = 2^m * 2^(j/64) * exp(r),  -s = (64 m + j) ln2/64 + r,  |r| <= ln2/128
+    const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: adds round-to-nearest-integer
+    const double NEG_L2E64 = -92.33248261689366;        // -64 / ln2
+    const double LN2_64_HI = 0.010830424667801708;      // ln2/64, 29 significant bits (k * HI exact)
+    const double LN2_64_LO = 2.8447437476627285e-11;
+    const double kd = fma(s, NEG_L2E64, MAGIC);
+    const int k = __double2loint(kd);
+    const double kf = kd - MAGIC;
+    double r = fma(kf, -LN2_64_HI, -s);
+    r = fma(kf, -LN2_64_LO, r);
+    double q = fma(1.0 / 120.0, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    const double p = fma(q, r, 1.0);
+    const double v = tab[k & (EXP_TAB_SIZE - 1)] * p;   // in [1, 2)
+    const int hi = __double2hiint(v) + ((k >> 6) << 20);  // scale by 2^m on the exponent field (ALU pipe)
+    const double res = __hiloint2double(hi, __double2loint(v));
+    // below 1e-304: flush (the exponent trick would wrap); integer compare on the high word keeps it off the FP64 pipe
+    return __double2hiint(s) > 0x4085E000 ? 0.0 : res;   // s > 700
+}
+
+__device__ __forceinline__ double sqrt_pos(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));   // MUFU.RSQ64H, rel err 2^-22
+    double g = a * y, h = 0.5 * y;
+    const double e = fma(-g, h, 0.5);
+    g = fma(g, e, g);
+    h = fma(h, e, h);
+    const double d = fma(-g, g, a);
+    return fma(d, h, g);
+}
+
+__device__ __forceinline__ double div_pos(double a, double b) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));     // MUFU.RCP64H
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    const double q = a * y;
+    return fma(fma(-b, q, a), y, q);
+}
+
+__device__ __forceinline__ double clamp_min_pos(double a, double floor_) {
+    // max(a, floor_) for floor_ > 0 through the integer pipe: for non-negative doubles the high words order
+    // like signed ints, and a (slightly) negative a -- cancellation noise -- has a negative high word.
+    const int hi = max(__double2hiint(a), __double2hiint(floor_));
+    return __hiloint2double(hi, __double2loint(a));
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Kernel nonlinearities.  `dot` is sum_k x_k * zt_k where zt already carries the factor -2 for the
-// stationary families, so d2 = xn + zn + dot.  The output scale is applied once per output entry by
-// the caller (linearity), not per pair.
+// stationary families, so the squared distance is xn + zn + dot.  The host folds the family's constant
+// into the lengthscale (coordinates are multiplied by 1/sqrt2, 1, sqrt3, sqrt5 for RBF / Matern-1/2, -3/2,
+// -5/2), so here   RBF = exp(-d2),  M12 = exp(-r),  M32 = (1+r) exp(-r),  M52 = (1 + r + d2/3) exp(-r)
+// with r = sqrt(d2).  The output scale is applied once per output entry by the caller (linearity).
 // ---------------------------------------------------------------------------------------------------
 template <int FAM>
-__device__ __forceinline__ double kernel_value(double dot, double xn, double zn) {
-    if (FAM == SOBER_TANIMOTO) {
-        const double eps = 1e-6;
-        double v = (dot + eps) / (eps + xn + zn - dot);
-        return fmax(v, 0.0);
-    }
-    double d2 = fmax(xn + zn + dot, 0.0);
+__device__ __forceinline__ double stationary_value(double d2, const double* __restrict__ tab) {
     if (FAM == SOBER_RBF) {
-        return exp(-0.5 * d2);
+        return exp_neg(clamp_min_pos(d2, 0.0), tab);
     }
-    double r = sqrt(fmax(d2, 1e-30));
-    if (FAM == SOBER_MATERN12) {
-        return exp(-r);
-    }
-    if (FAM == SOBER_MATERN32) {
-        double s = 1.7320508075688772 * r;
-        return (1.0 + s) * exp(-s);
-    }
-    // Matern-5/2
-    double s = 2.23606797749979 * r;
-    return (1.0 + s + (5.0 / 3.0) * (r * r)) * exp(-s);
+    const double a = clamp_min_pos(d2, 1e-30);
+    const double r = sqrt_pos(a);
+    const double ex = exp_neg(r, tab);
+    if (FAM == SOBER_MATERN12) return ex;
+    if (FAM == SOBER_MATERN32) return (1.0 + r) * ex;
+    return fma(a, 1.0 / 3.0, 1.0 + r) * ex;
+}
+
+__device__ __forceinline__ double tanimoto_value(double dot, double xn, double zn) {
+    const double eps = 1e-6;
+    const double v = div_pos(dot + eps, (eps + xn) + (zn - dot));
+    return fmax(v, 0.0);
+}
+
+template <int FAM>
+__device__ __forceinline__ double kernel_value(double dot, double xn, double zn, const double* __restrict__ tab) {
+    if (FAM == SOBER_TANIMOTO) return tanimoto_value(dot, xn, zn);
+    return stationary_value<FAM>((xn + zn) + dot, tab);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TMA 1-D bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
 }
 
 }  // namespace sober

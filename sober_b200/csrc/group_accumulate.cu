@@ -6,10 +6,13 @@
 // the (S x L) accumulator; nothing of size N x L ever exists.
 //
 // Two kernels share one contract:
-//   * group_small  : d <= 8.  Landmarks live in registers (one lane = TL landmarks), the warp walks the rows
-//                    of its TG groups, candidate records are warp-uniform (broadcast) loads.  FP64-pipe bound.
-//   * group_tiled  : any d.  64 landmarks x 64 groups per CTA, the <x, z> contraction runs over d in chunks of
-//                    16 staged through shared memory, 4x4 register tile per thread.
+//   * group_records : d <= 8, record layout.  A CTA owns TG adjacent groups and up to 8*32*TL landmarks (one lane
+//                     = TL landmarks held in registers).  The candidate records of its rows are staged into
+//                     shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier, 3 stages) issued by one
+//                     thread; every warp then reads each record as a broadcast LDS and evaluates TL x TG kernel
+//                     values.  FP64-pipe bound: ~28 FP64 instructions per Matern-5/2 evaluation (common.cuh).
+//   * group_tiled   : any d, indexed layout.  64 landmarks x 64 groups per CTA, the <x, z> contraction runs over
+//                     d in chunks of 16 staged through shared memory, 4x4 register tile per thread.
 // Rows are split across gridDim.z; partial sums go to a workspace and are reduced in a fixed order
 // (deterministic: no atomics), which also applies the output scale.
 #include "common.cuh"
@@ -23,8 +26,10 @@ struct GroupParams {
     int64_t xn_stride;
     const int32_t* idx;
     const double* mu;
+    const double* rec;
     int64_t n_local, pos0, ES;
     int S, L, d;
+    int unit_weights;
     const double* Zt;
     const double* zn;
     double* out;       // [nsplit][S][L]  (or At itself when nsplit == 1)
@@ -34,15 +39,69 @@ struct GroupParams {
 };
 
 // -------------------------------------------------------------------------------------------------
-// small-d register kernel
+// record kernel (small d)
 // -------------------------------------------------------------------------------------------------
+constexpr int REC_WARPS = 8;
+constexpr int REC_THREADS = REC_WARPS * 32;
+constexpr int REC_ROWS = 16;    // rows per pipeline stage
+constexpr int REC_STAGES = 3;
+
 template <int D, int FAM, int TL, int TG>
-__global__ void __launch_bounds__(128) group_small_kernel(const GroupParams p) {
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+__global__ void __launch_bounds__(REC_THREADS) group_records_kernel(const GroupParams p) {
+    constexpr int LDR = (D + 3) / 2 * 2;  // d + 2 rounded up to even
+    __shared__ __align__(16) double buf[REC_STAGES][REC_ROWS][TG][LDR];
+    __shared__ __align__(8) uint64_t bars[REC_STAGES];
+    __shared__ double tab[EXP_TAB_SIZE];
+
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
     const int g0 = blockIdx.x * TG;
-    const int l0 = (blockIdx.y * 4 + warp) * (32 * TL);
-    if (l0 >= p.L) return;  // whole warp out of range (no block-level sync in this kernel)
+    const int l0 = (blockIdx.y * REC_WARPS + warp) * (32 * TL);
+    const bool active = l0 < p.L;
+
+    load_exp_table(tab, t, REC_THREADS);
+    if (t == 0) {
+        for (int s = 0; s < REC_STAGES; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int64_t r0 = p.row_begin + (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t r1 = min(p.row_end, r0 + p.rows_per_split);
+    const int64_t hi = p.pos0 + p.n_local;
+    const int nchunks = (int)((r1 - r0 + REC_ROWS - 1) / REC_ROWS);
+    const int jmax = min(TG, p.S - g0);   // groups of this CTA that exist
+
+    // valid group interval [ja, jb) of row e: positions e*S + g0 + j that this device owns
+    auto interval = [&](int64_t e, int& ja, int& jb) {
+        const int64_t base = e * p.S + g0;
+        const int64_t a = max((int64_t)0, p.pos0 - base);
+        const int64_t b = min((int64_t)jmax, hi - base);
+        ja = (int)min(a, (int64_t)TG);
+        jb = (int)max(b, (int64_t)ja);
+    };
+    auto issue = [&](int c) {   // one thread: TMA bulk copies of chunk c into its stage
+        const int stage = c % REC_STAGES;
+        const int64_t e0 = r0 + (int64_t)c * REC_ROWS;
+        const int nrows = (int)min((int64_t)REC_ROWS, r1 - e0);
+        uint32_t bytes = 0;
+        for (int r = 0; r < nrows; ++r) {
+            int ja, jb;
+            interval(e0 + r, ja, jb);
+            bytes += (uint32_t)(jb - ja) * LDR * 8;
+        }
+        mbar_expect_tx(&bars[stage], bytes);
+        for (int r = 0; r < nrows; ++r) {
+            int ja, jb;
+            interval(e0 + r, ja, jb);
+            if (jb > ja) {
+                const int64_t loc = (e0 + r) * p.S + g0 + ja - p.pos0;
+                bulk_g2s(&buf[stage][r][ja][0], p.rec + loc * LDR, (uint32_t)(jb - ja) * LDR * 8, &bars[stage]);
+            }
+        }
+    };
+    if (t == 0)
+        for (int c = 0; c < REC_STAGES && c < nchunks; ++c) issue(c);
 
     double zt[TL][D], zn[TL];
 #pragma unroll
@@ -53,51 +112,77 @@ __global__ void __launch_bounds__(128) group_small_kernel(const GroupParams p) {
         for (int k = 0; k < D; ++k) zt[i][k] = ok ? __ldg(p.Zt + (int64_t)l * D + k) : 0.0;
         zn[i] = ok ? __ldg(p.zn + l) : 0.0;
     }
-
-    double acc[TL][TG];
-    double tw[TG];
+    double acc[TL][TG], tw[TG];
 #pragma unroll
     for (int j = 0; j < TG; ++j) {
         tw[j] = 0.0;
 #pragma unroll
         for (int i = 0; i < TL; ++i) acc[i][j] = 0.0;
     }
+    const bool count_tw = (blockIdx.y == 0) && (t == 0);
 
-    const int64_t r0 = p.row_begin + (int64_t)blockIdx.z * p.rows_per_split;
-    const int64_t r1 = min(p.row_end, r0 + p.rows_per_split);
-    const int64_t hi = p.pos0 + p.n_local;
-
-    for (int64_t e = r0; e < r1; ++e) {
-        double x[TG][D], xn[TG], w[TG];
+    for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % REC_STAGES;
+        mbar_wait(&bars[stage], (uint32_t)((c / REC_STAGES) & 1));
+        const int64_t e0 = r0 + (int64_t)c * REC_ROWS;
+        const int nrows = (int)min((int64_t)REC_ROWS, r1 - e0);
+        if (active) {
+            for (int r = 0; r < nrows; ++r) {
+                int ja, jb;
+                interval(e0 + r, ja, jb);
+                if (ja == 0 && jb == TG) {
+                    // fast path: all TG candidates of the row, TL x TG independent chains
+                    double x[TG][D], xn[TG], w[TG];
 #pragma unroll
-        for (int j = 0; j < TG; ++j) {
-            const int g = g0 + j;
-            const int64_t pos = e * p.S + g;
-            const bool ok = (g < p.S) && (pos >= p.pos0) && (pos < hi);
-            const int64_t loc = pos - p.pos0;
-            int64_t row = 0;
-            w[j] = 0.0;
-            if (ok) {
-                row = p.idx ? (int64_t)__ldg(p.idx + loc) : loc;
-                w[j] = p.mu ? __ldg(p.mu + loc) : 1.0;
+                    for (int j = 0; j < TG; ++j) {
+                        const double* rp = &buf[stage][r][j][0];
+#pragma unroll
+                        for (int k = 0; k < D; ++k) x[j][k] = rp[k];
+                        xn[j] = rp[D];
+                        w[j] = p.unit_weights ? 1.0 : rp[D + 1];
+                    }
+                    double val[TL][TG];
+#pragma unroll
+                    for (int i = 0; i < TL; ++i)
+#pragma unroll
+                        for (int j = 0; j < TG; ++j) {
+                            double dot = (FAM == SOBER_TANIMOTO) ? 0.0 : zn[i];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) dot = fma(x[j][k], zt[i][k], dot);
+                            val[i][j] = (FAM == SOBER_TANIMOTO) ? tanimoto_value(dot, xn[j], zn[i])
+                                                                : stationary_value<FAM>(xn[j] + dot, tab);
+                        }
+#pragma unroll
+                    for (int i = 0; i < TL; ++i)
+#pragma unroll
+                        for (int j = 0; j < TG; ++j) acc[i][j] = fma(val[i][j], w[j], acc[i][j]);
+                    if (count_tw && (e0 + r) * p.S + g0 < p.ES) {
+#pragma unroll
+                        for (int j = 0; j < TG; ++j) tw[j] += w[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TG; ++j) {
+                        if (j < ja || j >= jb) continue;
+                        const double* rp = &buf[stage][r][j][0];
+                        const double xn = rp[D];
+                        const double w = p.unit_weights ? 1.0 : rp[D + 1];
+#pragma unroll
+                        for (int i = 0; i < TL; ++i) {
+                            double dot = (FAM == SOBER_TANIMOTO) ? 0.0 : zn[i];
+#pragma unroll
+                            for (int k = 0; k < D; ++k) dot = fma(rp[k], zt[i][k], dot);
+                            const double v = (FAM == SOBER_TANIMOTO) ? tanimoto_value(dot, xn, zn[i])
+                                                                     : stationary_value<FAM>(xn + dot, tab);
+                            acc[i][j] = fma(v, w, acc[i][j]);
+                        }
+                        if (count_tw && (e0 + r) * p.S + g0 + j < p.ES) tw[j] += w;
+                    }
+                }
             }
-            const double* xr = p.X + row * p.ldx;
-#pragma unroll
-            for (int k = 0; k < D; ++k) x[j][k] = ok ? __ldg(xr + k) : 0.0;
-            xn[j] = ok ? __ldg(p.xn + row * p.xn_stride) : 0.0;
-            if (pos < p.ES) tw[j] += w[j];
         }
-#pragma unroll
-        for (int j = 0; j < TG; ++j) {
-#pragma unroll
-            for (int i = 0; i < TL; ++i) {
-                double dot = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) dot = fma(x[j][k], zt[i][k], dot);
-                const double kv = kernel_value<FAM>(dot, xn[j], zn[i]);
-                acc[i][j] = fma(kv, w[j], acc[i][j]);
-            }
-        }
+        __syncthreads();   // every warp is done with this stage before it is refilled
+        if (t == 0 && c + REC_STAGES < nchunks) issue(c + REC_STAGES);
     }
 
     double* out = p.out + (int64_t)blockIdx.z * p.S * p.L;
@@ -110,12 +195,12 @@ __global__ void __launch_bounds__(128) group_small_kernel(const GroupParams p) {
             const int l = l0 + lane + 32 * i;
             if (l < p.L) out[(int64_t)g * p.L + l] = acc[i][j] * p.scale;
         }
-        if (blockIdx.y == 0 && warp == 0 && lane == 0) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw[j];
+        if (count_tw) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw[j];
     }
 }
 
 // -------------------------------------------------------------------------------------------------
-// generic tiled kernel
+// generic tiled kernel (indexed layout)
 // -------------------------------------------------------------------------------------------------
 constexpr int TM = 64;   // landmarks per CTA
 constexpr int TN = 64;   // groups per CTA
@@ -128,11 +213,13 @@ __global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
     __shared__ double Xs[KC][LDS_ROW];
     __shared__ double s_w[TN], s_xn[TN];
     __shared__ int64_t s_row[TN];
+    __shared__ double tab[EXP_TAB_SIZE];
 
     const int t = threadIdx.x;
     const int tx = t & 15, ty = t >> 4;
     const int g0 = blockIdx.x * TN;
     const int l0 = blockIdx.y * TM;
+    load_exp_table(tab, t, 256);
 
     double zn[4];
 #pragma unroll
@@ -211,7 +298,7 @@ __global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
             const double xn = s_xn[tx + 16 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double kv = kernel_value<FAM>(dot[i][j], xn, zn[i]);
+                const double kv = kernel_value<FAM>(dot[i][j], xn, zn[i], tab);
                 acc[i][j] = fma(kv, w, acc[i][j]);
             }
         }
@@ -273,35 +360,36 @@ __global__ void group_gram_kernel(const double* __restrict__ G, int64_t ldg, int
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
+constexpr int REC_TL = 4;
+constexpr int REC_TG = 2;
+
 struct Plan {
-    bool small;
-    int tl, tg;
+    bool records;
     dim3 grid, block;
     int nsplit;
     int64_t rows_per_split, row_begin, row_end;
 };
 
 static bool plan_group(const sober_group_args* a, Plan* pl) {
-    if (!a || a->S <= 0 || a->L <= 0 || a->d <= 0 || a->n_local < 0) return false;
+    if (!a || a->S <= 0 || a->L <= 0 || a->d <= 0 || a->n_local < 0 || a->pos0 < 0) return false;
     const int64_t hi = a->pos0 + a->n_local;
     pl->row_begin = a->pos0 / a->S;
     pl->row_end = a->n_local > 0 ? ceil_div(hi, a->S) : pl->row_begin;
     const int64_t rows = pl->row_end - pl->row_begin;
-    pl->small = (a->variant == 2) || (a->variant == 0 && a->d <= 8);
-    if (a->variant == 2 && a->d > 8) return false;
-    int64_t gx, gy;
-    if (pl->small) {
-        pl->tl = 2;
-        pl->tg = 4;
-        gx = ceil_div(a->S, pl->tg);
-        gy = ceil_div(a->L, 4 * 32 * pl->tl);
-        pl->block = dim3(128);
+    pl->records = a->rec != nullptr && a->variant != 1;
+    if (pl->records && (a->d > 8 || a->ldr != (a->d + 3) / 2 * 2)) return false;
+    int64_t gx, gy, target;
+    if (pl->records) {
+        gx = ceil_div(a->S, REC_TG);
+        gy = ceil_div(a->L, REC_WARPS * 32 * REC_TL);
+        pl->block = dim3(REC_THREADS);
+        target = (int64_t)sm_count() * 12;   // many more CTAs than SMs: the tail wave costs < 1/12
     } else {
         gx = ceil_div(a->S, TN);
         gy = ceil_div(a->L, TM);
         pl->block = dim3(256);
+        target = (int64_t)sm_count() * 8;
     }
-    const int64_t target = (int64_t)sm_count() * (pl->small ? 16 : 8);
     int64_t ns = ceil_div(target, gx * gy);
     if (ns > rows) ns = rows;
     if (ns < 1) ns = 1;
@@ -313,28 +401,28 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
 }
 
 template <int D, int FAM>
-static void launch_small(const Plan& pl, const GroupParams& p, cudaStream_t st) {
-    group_small_kernel<D, FAM, 2, 4><<<pl.grid, pl.block, 0, st>>>(p);
+static void launch_records(const Plan& pl, const GroupParams& p, cudaStream_t st) {
+    group_records_kernel<D, FAM, REC_TL, REC_TG><<<pl.grid, pl.block, 0, st>>>(p);
 }
 
 template <int FAM>
-static bool launch_small_d(const Plan& pl, const GroupParams& p, cudaStream_t st) {
+static bool launch_records_d(const Plan& pl, const GroupParams& p, cudaStream_t st) {
     switch (p.d) {
-        case 1: launch_small<1, FAM>(pl, p, st); return true;
-        case 2: launch_small<2, FAM>(pl, p, st); return true;
-        case 3: launch_small<3, FAM>(pl, p, st); return true;
-        case 4: launch_small<4, FAM>(pl, p, st); return true;
-        case 5: launch_small<5, FAM>(pl, p, st); return true;
-        case 6: launch_small<6, FAM>(pl, p, st); return true;
-        case 7: launch_small<7, FAM>(pl, p, st); return true;
-        case 8: launch_small<8, FAM>(pl, p, st); return true;
+        case 1: launch_records<1, FAM>(pl, p, st); return true;
+        case 2: launch_records<2, FAM>(pl, p, st); return true;
+        case 3: launch_records<3, FAM>(pl, p, st); return true;
+        case 4: launch_records<4, FAM>(pl, p, st); return true;
+        case 5: launch_records<5, FAM>(pl, p, st); return true;
+        case 6: launch_records<6, FAM>(pl, p, st); return true;
+        case 7: launch_records<7, FAM>(pl, p, st); return true;
+        case 8: launch_records<8, FAM>(pl, p, st); return true;
         default: return false;
     }
 }
 
 template <int FAM>
 static bool launch_family(const Plan& pl, const GroupParams& p, cudaStream_t st) {
-    if (pl.small) return launch_small_d<FAM>(pl, p, st);
+    if (pl.records) return launch_records_d<FAM>(pl, p, st);
     group_tiled_kernel<FAM><<<pl.grid, pl.block, 0, st>>>(p);
     return true;
 }
@@ -354,7 +442,8 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
                                       void* stream) {
     Plan pl;
     if (!plan_group(a, &pl)) return SOBER_ERR_ARG;
-    if (!a->X || !a->xn || !a->Zt || !a->zn || !a->At || !a->totw) return SOBER_ERR_ARG;
+    if (!a->Zt || !a->zn || !a->At || !a->totw) return SOBER_ERR_ARG;
+    if (!pl.records && (!a->X || !a->xn)) return SOBER_ERR_ARG;
     if (a->family < SOBER_RBF || a->family > SOBER_TANIMOTO) return SOBER_ERR_UNSUPPORTED;
     const int64_t need = sober_group_accumulate_workspace(a);
     if (need > workspace_bytes || (need > 0 && !workspace)) return SOBER_ERR_WORKSPACE;
@@ -369,9 +458,10 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
 
     GroupParams p;
     p.X = a->X; p.ldx = a->ldx; p.xn = a->xn; p.xn_stride = a->xn_stride;
-    p.idx = a->idx; p.mu = a->mu;
+    p.idx = a->idx; p.mu = a->mu; p.rec = a->rec;
     p.n_local = a->n_local; p.pos0 = a->pos0; p.ES = a->ES;
     p.S = a->S; p.L = a->L; p.d = a->d;
+    p.unit_weights = a->unit_weights;
     p.Zt = a->Zt; p.zn = a->zn;
     p.row_begin = pl.row_begin; p.row_end = pl.row_end; p.rows_per_split = pl.rows_per_split;
     double* ws = (double*)workspace;

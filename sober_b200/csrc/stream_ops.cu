@@ -45,6 +45,26 @@ __global__ void prepare_rows_wide_kernel(const double* __restrict__ X, int64_t l
     for (int64_t k = d + 1 + lane; k < ldp; k += 32) p[k] = 0.0;
 }
 
+// ---- records: gather + transform + norm + weight, one 16-byte-aligned row per alive point -----------------
+__global__ void make_records_kernel(const double* __restrict__ X, int64_t ldx, int d, const double* __restrict__ center,
+                                    const double* __restrict__ inv_ls, const int32_t* __restrict__ idx,
+                                    const double* __restrict__ mu, int64_t m, double* __restrict__ rec, int64_t ldr) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const int64_t row = idx ? (int64_t)idx[j] : j;
+    const double* x = X + row * ldx;
+    double* r = rec + j * ldr;
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double u = (x[k] - center[k]) * inv_ls[k];
+        r[k] = u;
+        s = fma(u, u, s);
+    }
+    r[d] = s;
+    r[d + 1] = mu ? mu[j] : 1.0;
+    for (int64_t k = d + 2; k < ldr; ++k) r[k] = 0.0;
+}
+
 __global__ void row_sqnorm_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int d,
                                   double* __restrict__ out) {
     const int lane = threadIdx.x & 31;
@@ -162,7 +182,8 @@ constexpr int UC_ITEMS = 4;
 __global__ void __launch_bounds__(UC_THREADS) update_compact_kernel(
     const int32_t* __restrict__ idx_in, const double* __restrict__ mu_in, int64_t n_local, int64_t pos0, int64_t ES,
     int S, const double* __restrict__ wstar, const double* __restrict__ totw, const int32_t* __restrict__ rank, int K,
-    int tail_keep, int64_t new_pos0, int32_t* __restrict__ idx_out, double* __restrict__ mu_out) {
+    int tail_keep, int64_t new_pos0, int32_t* __restrict__ idx_out, double* __restrict__ mu_out,
+    const double* __restrict__ rec_in, double* __restrict__ rec_out, int ldr, int d) {
     const int64_t tile0 = (int64_t)blockIdx.x * (UC_THREADS * UC_ITEMS);
     const int64_t p_tile = pos0 + tile0;
     const int64_t e_tile = p_tile / S;                 // one 64-bit division per thread, not per element
@@ -189,8 +210,19 @@ __global__ void __launch_bounds__(UC_THREADS) update_compact_kernel(
         }
         dst -= new_pos0;
         // (mu * w*) / totw -- two roundings, SOBER/_rchq.py:204-205
-        mu_out[dst] = __ddiv_rn(__dmul_rn(mu_in[j], wstar[g]), totw[g]);
+        const double w_new = __ddiv_rn(__dmul_rn(mu_in[j], wstar[g]), totw[g]);
+        mu_out[dst] = w_new;
         idx_out[dst] = idx_in[j];
+        if (rec_in) {   // the record row travels with its point (16-byte vector copies), weight slot refreshed
+            const double2* src = reinterpret_cast<const double2*>(rec_in + j * ldr);
+            double2* out = reinterpret_cast<double2*>(rec_out + dst * ldr);
+            for (int k = 0; k < ldr / 2; ++k) {
+                double2 v = src[k];
+                if (2 * k == d + 1) v.x = w_new;
+                if (2 * k + 1 == d + 1) v.y = w_new;
+                out[k] = v;
+            }
+        }
     }
 }
 
@@ -231,6 +263,18 @@ extern "C" int sober_prepare_points(const double* X, int64_t ldx, int64_t n, int
     return SOBER_OK;
 }
 
+extern "C" int sober_make_records(const double* X, int64_t ldx, int32_t d, const double* center, const double* inv_ls,
+                                  const int32_t* idx, const double* mu, int64_t m, double* rec, int64_t ldr,
+                                  void* stream) {
+    if (m < 0 || d <= 0 || ldx < d || ldr < d + 2 || (ldr & 1) || (m > 0 && (!X || !rec || !center || !inv_ls)))
+        return SOBER_ERR_ARG;
+    if (m == 0) return SOBER_OK;
+    make_records_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, d, center, inv_ls, idx, mu,
+                                                                                      m, rec, ldr);
+    SOBER_LAUNCH_CHECK("make_records");
+    return SOBER_OK;
+}
+
 extern "C" int sober_row_sqnorm(const double* X, int64_t ldx, int64_t n, int32_t d, double* out, void* stream) {
     if (n < 0 || d <= 0 || ldx < d || (n > 0 && (!X || !out))) return SOBER_ERR_ARG;
     if (n == 0) return SOBER_OK;
@@ -265,14 +309,17 @@ extern "C" int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_o
 extern "C" int sober_update_compact(const int32_t* idx_in, const double* mu_in, int64_t n_local, int64_t pos0,
                                     int64_t ES, int32_t S, const double* wstar, const double* totw,
                                     const int32_t* rank, int32_t K, int32_t tail_keep, int64_t new_pos0,
-                                    int32_t* idx_out, double* mu_out, void* stream) {
+                                    int32_t* idx_out, double* mu_out, const double* rec_in, double* rec_out,
+                                    int64_t ldr, int32_t d, void* stream) {
     if (n_local < 0 || S <= 0 || K < 0 || ES < 0 || ES % S != 0 || pos0 < 0) return SOBER_ERR_ARG;
     if (n_local == 0) return SOBER_OK;
     if (!idx_in || !mu_in || !wstar || !totw || !rank || !idx_out || !mu_out) return SOBER_ERR_ARG;
     if (pos0 + n_local >= ((int64_t)1 << 31)) return SOBER_ERR_UNSUPPORTED;
+    if (rec_in && (!rec_out || ldr < d + 2 || (ldr & 1))) return SOBER_ERR_ARG;
     const int64_t tile = UC_THREADS * UC_ITEMS;
     update_compact_kernel<<<(unsigned)ceil_div(n_local, tile), UC_THREADS, 0, (cudaStream_t)stream>>>(
-        idx_in, mu_in, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, idx_out, mu_out);
+        idx_in, mu_in, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, idx_out, mu_out, rec_in, rec_out,
+        (int)ldr, d);
     SOBER_LAUNCH_CHECK("update_compact");
     return SOBER_OK;
 }

@@ -16,20 +16,19 @@ RBF, MATERN12, MATERN32, MATERN52, TANIMOTO = range(5)
 
 
 def kernel_values(dot, xn, zn, family):
-    """dot: (m, L) = x . zt ; xn: (m, 1) ; zn: (1, L)"""
+    """dot: (m, L) = x . zt ; xn: (m, 1) ; zn: (1, L).  Same convention as csrc/common.cuh: the family constant
+    is already folded into the coordinates (sober_b200._lib.FAMILY_SCALE)."""
     if family == TANIMOTO:
         return ((dot + 1e-6) / (1e-6 + xn + zn - dot)).clamp_min(0)
     d2 = (xn + zn + dot).clamp_min(0)
     if family == RBF:
-        return torch.exp(-0.5 * d2)
+        return torch.exp(-d2)
     r = d2.clamp_min(1e-30).sqrt()
     if family == MATERN12:
         return torch.exp(-r)
     if family == MATERN32:
-        s = math.sqrt(3.0) * r
-        return (1 + s) * torch.exp(-s)
-    s = math.sqrt(5.0) * r
-    return (1 + s + (5.0 / 3.0) * r * r) * torch.exp(-s)
+        return (1 + r) * torch.exp(-r)
+    return (1 + r + d2 / 3.0) * torch.exp(-r)
 
 
 class TorchOps:
@@ -48,6 +47,17 @@ class TorchOps:
         P[:, d] = (P[:, :d] ** 2).sum(-1)
         return PointSet(P, ldp, P[:, d], ldp, n, d)
 
+    def make_records(self, X, center, inv_ls, idx=None, mu=None):
+        d = X.shape[1]
+        rows = X if idx is None else X[idx.long()]
+        m = rows.shape[0]
+        ldr = (d + 3) // 2 * 2
+        rec = torch.zeros((m, ldr), dtype=torch.float64)
+        rec[:, :d] = (rows - center) * inv_ls
+        rec[:, d] = (rec[:, :d] ** 2).sum(-1)
+        rec[:, d + 1] = 1.0 if mu is None else mu
+        return PointSet(None, 0, None, 0, m, d, rec=rec, ldr=ldr)
+
     def raw_points(self, X):
         n, d = X.shape
         return PointSet(X, X.stride(0), (X * X).sum(-1), 1, n, d)
@@ -56,16 +66,20 @@ class TorchOps:
         idx = torch.nonzero(mu != 0).reshape(-1).to(torch.int32)
         return idx, mu[idx.long()].clone(), int(idx.numel())
 
-    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None):
+    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None, rec=None, unit_weights=False):
         L, d = lm.L, lm.d
         at = torch.zeros((S, L), dtype=torch.float64)
         totw = torch.zeros(S, dtype=torch.float64)
         if n_local == 0:
             return at, totw
-        rows = torch.arange(n_local) if idx is None else idx[:n_local].long()
-        w = torch.ones(n_local, dtype=torch.float64) if mu is None else mu[:n_local]
-        x = pts.rows[rows, :d]
-        xn = pts.xn[rows].reshape(-1, 1)
+        if rec is not None:
+            x, xn = rec[:n_local, :d], rec[:n_local, d].reshape(-1, 1)
+            w = torch.ones(n_local, dtype=torch.float64) if unit_weights else rec[:n_local, d + 1]
+        else:
+            rows = torch.arange(n_local) if idx is None else idx[:n_local].long()
+            w = torch.ones(n_local, dtype=torch.float64) if mu is None else mu[:n_local]
+            x = pts.rows[rows, :d]
+            xn = pts.xn[rows].reshape(-1, 1)
         kv = kernel_values(x @ lm.zt.T, xn, lm.zn.reshape(1, -1), lm.family) * w.reshape(-1, 1)
         pos = pos0 + torch.arange(n_local)
         at.index_add_(0, pos % S, kv)
@@ -90,7 +104,8 @@ class TorchOps:
             piv[:len(removed)] = torch.tensor(removed, dtype=torch.int32)
             return piv, torch.tensor([len(removed)], dtype=torch.int32)
 
-    def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out):
+    def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out,
+                       rec=None, d=0):
         pos = pos0 + torch.arange(n_local)
         g = torch.where(pos < ES, pos % S, torch.full_like(pos, S - 1))
         keep = torch.where(pos < ES, wstar[g] > 0, torch.full_like(pos, bool(tail_keep), dtype=torch.bool))
@@ -99,7 +114,12 @@ class TorchOps:
         mu_out = torch.zeros(n_out, dtype=torch.float64)
         idx_out[dst[keep]] = idx[:n_local][keep]
         mu_out[dst[keep]] = (mu[:n_local][keep] * wstar[g[keep]]) / totw[g[keep]]
-        return idx_out, mu_out
+        rec_out = None
+        if rec is not None:
+            rec_out = torch.zeros((n_out, rec.shape[1]), dtype=torch.float64)
+            rec_out[dst[keep]] = rec[:n_local][keep]
+            rec_out[:, d + 1] = mu_out
+        return idx_out, mu_out, rec_out
 
     def scatter_result(self, dst, idx, w):
         dst.zero_()

@@ -28,39 +28,45 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
 
 
+def scaled(spec, Z, dev):
+    """centre / reciprocal lengthscale (family constant folded in) the way Recombiner.run builds them."""
+    from sober_b200 import _lib
+    d = Z.shape[1]
+    if spec.stationary:
+        return Z.mean(0).contiguous(), (spec.inv_ls.to(dev) * _lib.FAMILY_SCALE[spec.family]).expand(d).contiguous()
+    return torch.zeros(d, dtype=torch.float64, device=dev), torch.ones(d, dtype=torch.float64, device=dev)
+
+
 def spec_tables(rec, case, dev):
     """Landmark table / prepared points for a fixture, built the way Recombiner does."""
     from sober_b200._kernel_spec import introspect
     kern = case.kernel()
     spec = introspect(kern)
-    Z = case.Z
-    center = inv_ls = None
-    if spec.stationary:
-        center = Z.mean(0).contiguous()
-        inv_ls = spec.inv_ls.to(dev).expand(Z.shape[1]).contiguous()
+    center, inv_ls = scaled(spec, case.Z, dev)
     return kern, spec, center, inv_ls
 
 
 # ------------------------------------------------------------------------------------------------------------
 # P0: Gram matrices, every family, both K1 variants
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1])     # 0: record/register kernel when d <= 8, 1: tiled kernel
 @pytest.mark.parametrize("name", ["matern6d_rest", "rbf2d_branin", "rbf_ard5d", "ising24_hamming", "tanimoto256"])
 def test_gram_matches_oracle(ops, cuda_device, name, variant):
-    from sober_b200 import Recombiner
+    from sober_b200 import Recombiner, configure
     case = Case(name, cuda_device)
-    if variant == 2 and case.X.shape[1] > 8:
+    if variant == 0 and case.X.shape[1] > 8:
         pytest.skip("register kernel covers d <= 8")
-    rec = Recombiner(ops)
-    kern, spec, center, inv_ls = spec_tables(rec, case, cuda_device)
-    ops.variant = variant
-    try:
-        table = rec._table(case.Z, spec, center, inv_ls)
-        got_zz = rec._gram_T(rec._points(case.Z, spec, center, inv_ls), table).T
-        sub = case.X[:777].contiguous()
-        got_zx = rec._gram_T(rec._points(sub, spec, center, inv_ls), table).T
-    finally:
-        ops.variant = 0
+    with configure(k1_variant=variant) as opts:
+        rec = Recombiner(ops, opts=opts)
+        ops.variant = variant
+        kern, spec, center, inv_ls = spec_tables(rec, case, cuda_device)
+        try:
+            table = rec._table(case.Z, spec, center, inv_ls)
+            got_zz = rec._gram_T(rec._points(case.Z, spec, center, inv_ls), table).T
+            sub = case.X[:777].contiguous()
+            got_zx = rec._gram_T(rec._points(sub, spec, center, inv_ls), table).T
+        finally:
+            ops.variant = 0
     assert rel(got_zz, case.K_raw) < 1e-10
     assert float((got_zz - case.K_raw).abs().max()) < 1e-12
     want = kern(case.Z, sub)
@@ -78,7 +84,7 @@ def test_gram_other_matern_orders(ops, cuda_device, nu):
     from sober_b200._kernel_spec import introspect
     spec = introspect(kern)
     rec = Recombiner(ops)
-    center, inv_ls = Z.mean(0).contiguous(), spec.inv_ls.to(cuda_device).expand(3).contiguous()
+    center, inv_ls = scaled(spec, Z, cuda_device)
     got = rec._gram_T(rec._points(X, spec, center, inv_ls), rec._table(Z, spec, center, inv_ls)).T
     want = kern(Z, X)
     # nu = 1/2 is not differentiable at r = 0: the expanded distance's rounding noise (1e-16 in d2 -> 1e-8 in r)
@@ -90,14 +96,15 @@ def test_gram_other_matern_orders(ops, cuda_device, nu):
 # ------------------------------------------------------------------------------------------------------------
 # P1: group sums per iteration (remainder quirk included), against the oracle's trace
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1])
 @pytest.mark.parametrize("name", LOOP_CASES)
 def test_group_accumulate_matches_oracle_trace(ops, cuda_device, name, variant):
-    from sober_b200 import Recombiner
+    from sober_b200 import Recombiner, configure
+    from sober_b200._rchq import Alive
     case = Case(name)                                   # oracle on the CPU
     if case.objective is not None:
         pytest.skip("objective branch covered end-to-end")
-    if variant == 2 and case.X.shape[1] > 8:
+    if variant == 0 and case.X.shape[1] > 8:
         pytest.skip("register kernel covers d <= 8")
     groups, updates = [], []
 
@@ -115,31 +122,33 @@ def test_group_accumulate_matches_oracle_trace(ops, cuda_device, name, variant):
     mass = [mu0[alive[0]]] + [u["mass_alive"] for u in updates]
 
     dcase = Case(name, cuda_device)
-    rec = Recombiner(ops)
-    kern, spec, center, inv_ls = spec_tables(rec, dcase, cuda_device)
     n = case.U.shape[0]
     S = 2 * (n + 1)
     ops.variant = variant
     try:
-        rec.basis = dcase.U
-        U, Uext, table = rec._nystrom(dcase.Z, case.b - 1, kern, spec, center, inv_ls)
-        pts = rec._points(dcase.X, spec, center, inv_ls)
-        for t, grp in enumerate(groups):
-            idx = alive[t].to(cuda_device, torch.int32)
-            m = mass[t].to(cuda_device)
-            R = len(idx)
-            E = R // S
-            at, totw = ops.group_accumulate(pts, table, idx, m, R, 0, E * S, S)
-            if spec.mode == "kernel":
-                assert rel(at.T.cpu(), grp["A"]) < 1e-10
-            # projected (unnormalised) barycentres incl. the second count of the remainder
-            bary = at @ Uext.T
-            if R > E * S:
-                tail_at, tail_tw = ops.group_accumulate(pts, table, idx[E * S:], m[E * S:], R - E * S, 0, R - E * S, 1)
-                bary[S - 1] += (tail_at @ Uext.T)[0]
-                totw[S - 1] += tail_tw[0]
-            assert rel(totw.cpu(), grp["totw"]) < 1e-13
-            assert rel(bary.cpu(), grp["Xt_unnormalised"]) < 1e-10
+        with configure(k1_variant=variant) as opts:
+            rec = Recombiner(ops, opts=opts, basis=dcase.U)
+            kern, spec, center, inv_ls = spec_tables(rec, dcase, cuda_device)
+            U, Uext, table = rec._nystrom(dcase.Z, case.b - 1, kern, spec, center, inv_ls)
+            records = rec._use_records(spec, dcase.X.shape[1])
+            st = {"spec": spec, "table": table, "pts": None if records else rec._points(dcase.X, spec, center, inv_ls)}
+            for t, grp in enumerate(groups):
+                idx = alive[t].to(cuda_device, torch.int32)
+                m = mass[t].to(cuda_device)
+                R = len(idx)
+                E = R // S
+                al = Alive(idx, m, ops.make_records(dcase.X, center, inv_ls, idx, m).rec if records else None)
+                at, totw = rec._accumulate(st, al, R, 0, E * S, S)
+                if spec.mode == "kernel":
+                    assert rel(at.T.cpu(), grp["A"]) < 1e-10
+                # projected (unnormalised) barycentres incl. the second count of the remainder
+                bary = at @ Uext.T
+                if R > E * S:
+                    tail_at, tail_tw = rec._accumulate(st, al.tail(E * S), R - E * S, 0, R - E * S, 1)
+                    bary[S - 1] += (tail_at @ Uext.T)[0]
+                    totw[S - 1] += tail_tw[0]
+                assert rel(totw.cpu(), grp["totw"]) < 1e-13
+                assert rel(bary.cpu(), grp["Xt_unnormalised"]) < 1e-10
     finally:
         ops.variant = 0
 
@@ -211,14 +220,22 @@ def test_update_compact_exact(ops, cuda_device, S, R, pos0):
     n_out = km.before(pos0 + n_local) - new_pos0
     rank = (torch.cumsum(kept.int(), 0) - kept.int()).to(torch.int32)
     d = lambda t: t.to(cuda_device)
-    idx_o, mu_o = ops.update_compact(d(idx), d(mu), n_local, pos0, ES, S, d(wstar), d(totw), d(rank), km.K,
-                                     km.tail_keep, new_pos0, n_out)
+    dim = 6 if S % 2 == 0 else 3                       # record strides 8 and 6 (one with a pad slot)
+    ldr = (dim + 3) // 2 * 2
+    rec = torch.rand(n_local, ldr, dtype=torch.float64, generator=g)
+    rec[:, dim + 1] = mu
+    idx_o, mu_o, rec_o = ops.update_compact(d(idx), d(mu), n_local, pos0, ES, S, d(wstar), d(totw), d(rank), km.K,
+                                            km.tail_keep, new_pos0, n_out, rec=d(rec), d=dim)
     pos = pos0 + torch.arange(n_local)
     grp = torch.where(pos < ES, pos % S, torch.full_like(pos, S - 1))
     live = torch.where(pos < ES, kept[grp], torch.full_like(pos, km.tail_keep, dtype=torch.bool))
     assert int(live.sum()) == n_out
     assert torch.equal(idx_o.cpu(), idx[live])
-    assert torch.equal(mu_o.cpu(), (mu[live] * wstar[grp[live]]) / totw[grp[live]])
+    want_mu = (mu[live] * wstar[grp[live]]) / totw[grp[live]]
+    assert torch.equal(mu_o.cpu(), want_mu)
+    want_rec = rec[live].clone()
+    want_rec[:, dim + 1] = want_mu
+    assert torch.equal(rec_o.cpu(), want_rec)
 
 
 @pytest.mark.parametrize("n,d", [(1000, 6), (333, 2), (257, 24), (100, 300)])
@@ -233,6 +250,25 @@ def test_prepare_points_and_norms(ops, cuda_device, n, d):
     assert float((pts.xn - (want * want).sum(-1)).abs().max()) < 1e-12 * d
     raw = ops.raw_points(X)
     assert float((raw.xn - (X * X).sum(-1)).abs().max()) < 1e-12 * d
+
+
+@pytest.mark.parametrize("n,d", [(5000, 6), (999, 3), (1234, 8), (77, 1)])
+def test_make_records(ops, cuda_device, n, d):
+    g = torch.Generator().manual_seed(n)
+    X = torch.randn(n, d, dtype=torch.float64, generator=g).to(cuda_device)
+    c = torch.randn(d, dtype=torch.float64, generator=g).to(cuda_device)
+    s = (torch.rand(d, dtype=torch.float64, generator=g) + 0.5).to(cuda_device)
+    idx = torch.sort(torch.randperm(n, generator=g)[:n // 2])[0].to(cuda_device, torch.int32)
+    mu = torch.rand(n // 2, dtype=torch.float64, generator=g).to(cuda_device)
+    ps = ops.make_records(X, c, s, idx, mu)
+    want = (X[idx.long()] - c) * s
+    assert ps.rec.shape == (n // 2, (d + 3) // 2 * 2)
+    assert torch.equal(ps.rec[:, :d], want)
+    assert float((ps.rec[:, d] - (want * want).sum(-1)).abs().max()) < 1e-12 * d
+    assert torch.equal(ps.rec[:, d + 1], mu)
+    assert bool((ps.rec[:, d + 2:] == 0).all())
+    full = ops.make_records(X, c, s)
+    assert full.rec.shape[0] == n and bool((full.rec[:, d + 1] == 1).all())
 
 
 def test_scatter_result(ops, cuda_device):
