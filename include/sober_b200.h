@@ -149,6 +149,22 @@ int64_t sober_car_workspace(int32_t k);
 int sober_car_eliminate(double* basis, int32_t k, int32_t S, double* mu, int32_t* pivots_out, int32_t* steps_out,
                         void* sync_ws, int64_t sync_ws_bytes, void* stream);
 
+/* The whole Caratheodory reduction (SOBER/_rchq.py:224-270) in ONE kernel on one thread-block cluster, state
+ * resident in distributed shared memory (sizes up to roughly S <= 440 on 8 CTAs, S <= 630 on 16):
+ *   basis == NULL: Householder QR of design (S x np, row-major, = [1 | X]) -> null-space basis -> elimination
+ *                  (LAPACK reflector convention: the basis equals the trailing columns of the complete Q);
+ *   basis != NULL: elimination only, on the given k x S rows (k = S - np), design ignored.
+ * exact != 0 keeps the reference's unfused (phi_j * v_i) / v_j arithmetic in the elimination (bit-identical pivots
+ * for the same basis); exact == 0 uses one division per row and an FMA per element.
+ * mu (S) is updated in place; info (2 int32, may be NULL): [0] elimination steps taken, [1] 1 if the QR ran.
+ * sober_car_cluster_fits returns the cluster size that would be used (0: does not fit -> use the two-step path). */
+int sober_car_cluster_fits(int32_t S, int32_t np, int32_t have_basis);
+int sober_car_cluster(const double* design, const double* basis, int32_t S, int32_t np, double* mu, int32_t exact,
+                      int32_t* info, void* stream);
+/* Same, with 12 int64 cycle counters of CTA 0 / thread 0 written to prof (diagnostics: where a step's time goes). */
+int sober_car_cluster_profiled(const double* design, const double* basis, int32_t S, int32_t np, double* mu,
+                               int32_t exact, int32_t* info, int64_t* prof, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Weight update + compaction of the alive-list (SOBER/_rchq.py:198-221).
  *   For local position j (global p = pos0 + j):

@@ -21,11 +21,25 @@ def nullspace_rows(design, how):
 
 
 def caratheodory(ops, feats, mass, how, nullspace=None):
-    """feats (S x n), mass (S,) -> weights (S,) with zeros at eliminated points; preserves [1 feats]^T mass."""
+    """feats (S x n), mass (S,) -> weights (S,) with zeros at eliminated points; preserves [1 feats]^T mass.
+
+    Small problems (the whole state fits the distributed shared memory of one thread-block cluster) run as ONE
+    kernel, ``sober_car_cluster``: QR + null space + elimination for ``how="qr"``, the elimination alone -- with the
+    reference's exact arithmetic -- on a torch-SVD / injected basis otherwise.  Larger ones take the null space from
+    torch.linalg and the persistent multi-CTA elimination kernel."""
     ones = torch.ones((feats.shape[0], 1), dtype=feats.dtype, device=feats.device)
-    design = torch.cat([ones, feats], dim=1)
-    rows = nullspace(design) if nullspace is not None else nullspace_rows(design, how)
+    design = torch.cat([ones, feats], dim=1).contiguous()
+    pts, dim = design.shape
     out = mass.clone().contiguous()
-    if rows.shape[0] > 0:
+    if pts <= dim:
+        return out
+    fits = getattr(ops, "car_cluster_fits", None)
+    if nullspace is None and how == "qr" and fits is not None and fits(pts, dim, False):
+        ops.car_cluster(out, design=design)
+        return out
+    rows = nullspace(design) if nullspace is not None else nullspace_rows(design, how)
+    if fits is not None and fits(pts, dim, True):
+        ops.car_cluster(out, basis_rows=rows, exact=True)
+    else:
         ops.car_eliminate(rows, out)
     return out

@@ -200,6 +200,29 @@ class CudaOps:
         self.launches += 1
         return (piv, steps) if want_pivots else None
 
+    def car_cluster_fits(self, S, n_prime, have_basis):
+        """Cluster size the fused CAR kernel would use for this shape, 0 if it does not fit in distributed smem."""
+        with torch.cuda.device(self.device):
+            return int(self.lib.sober_car_cluster_fits(int(S), int(n_prime), int(bool(have_basis))))
+
+    def car_cluster(self, mass, design=None, basis_rows=None, exact=False):
+        """Fused CAR on one thread-block cluster: QR null space + elimination from ``design`` (S x n'), or the
+        elimination alone on ``basis_rows`` (k x S).  ``mass`` (S,) is reduced in place."""
+        src = design if basis_rows is None else basis_rows
+        assert src.is_contiguous() and mass.is_contiguous()
+        if basis_rows is None:
+            S, n_prime = design.shape
+        else:
+            S = basis_rows.shape[1]
+            n_prime = S - basis_rows.shape[0]
+        with torch.cuda.device(self.device):
+            t0 = self._begin("car_cluster")
+            check(self.lib.sober_car_cluster(_ptr(design) if basis_rows is None else None, _ptr(basis_rows), int(S),
+                                             int(n_prime), _ptr(mass), int(bool(exact)), None, self._stream()),
+                  "car_cluster")
+            self._end("car_cluster", t0, (S - n_prime) + (0 if basis_rows is not None else 2 * n_prime))
+        self.launches += 1
+
     # -- update + compaction ----------------------------------------------------------------------------------
     def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out,
                        rec=None, d=0):

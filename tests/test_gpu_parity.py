@@ -177,6 +177,47 @@ def test_car_elimination_bitwise(ops, cuda_device, name, force_global):
         os.environ.pop("SOBER_B200_CAR_FORCE_GLOBAL", None)
 
 
+@pytest.mark.parametrize("name", STABLE + ["rbf2d_branin"])
+def test_car_cluster_elimination_bitwise(ops, cuda_device, name):
+    """The cluster-resident kernel in EXACT mode on the reference's own null-space bases: bit-identical."""
+    case = Case(name, cuda_device)
+    if case.n_car == 0:
+        pytest.skip("no CAR call in this fixture")
+    for i in range(case.n_car):
+        phi = case.car(i, "Phi")
+        assert ops.car_cluster_fits(phi.shape[0], phi.shape[0] - phi.shape[1], True) > 0
+        mass = case.car(i, "mu").clone().contiguous()
+        ops.car_cluster(mass, basis_rows=phi.T.contiguous(), exact=True)
+        torch.cuda.synchronize()
+        keep = mass > 0
+        assert torch.equal(torch.nonzero(keep).reshape(-1), case.car(i, "idx"))
+        assert torch.equal(mass[keep], case.car(i, "w"))
+
+
+@pytest.mark.parametrize("S,n_prime", [(48, 24), (400, 200), (96, 41), (200, 100), (33, 7)])
+def test_car_cluster_fused_qr(ops, cuda_device, S, n_prime):
+    """QR + null space + elimination in one kernel vs LAPACK QR + the oracle's elimination: same support, same
+    weights, moments [1 X]^T w preserved to rounding."""
+    g = torch.Generator().manual_seed(S * 1000 + n_prime)
+    feats = torch.randn(S, n_prime - 1, dtype=torch.float64, generator=g) * \
+        torch.logspace(0, -5, n_prime - 1, dtype=torch.float64)            # columns spanning 5 decades
+    mass = torch.rand(S, dtype=torch.float64, generator=g)
+    mass /= mass.sum()
+    design = torch.cat([torch.ones(S, 1, dtype=torch.float64), feats], 1)
+    assert ops.car_cluster_fits(S, n_prime, False) > 0
+    got = mass.clone().to(cuda_device)
+    ops.car_cluster(got, design=design.to(cuda_device).contiguous())
+    torch.cuda.synchronize()
+    got = got.cpu()
+    want = mass.clone()
+    phi = torch.linalg.qr(design, mode="complete").Q[:, n_prime:]
+    oracle.eliminate(phi.clone(), want, oracle.Factory())
+    assert int((got > 0).sum()) <= n_prime
+    assert torch.equal(got > 0, want > 0)
+    assert float((got - want).abs().max()) < 1e-10
+    assert float((design.T @ got - design.T @ mass).abs().max()) < 1e-13
+
+
 def test_car_early_stop_guard(ops, cuda_device):
     """No positive entry in the leading null vector -> stop (SOBER/_rchq.py:241-242)."""
     rows = -torch.ones((3, 8), dtype=torch.float64, device=cuda_device)
