@@ -145,11 +145,11 @@ class Recombiner:
                 gram = gram - k_zo_w @ k_oz
             gram = 0.5 * (gram + gram.T)
             gram = _psd.repair(gram, o.gate, assume_asymmetric=True)
-            U = _nystrom.lowrank_basis(gram, n_basis)
+            U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr)
         else:
             gram = kernel(Z, Z)
             gram = _psd.repair(gram, o.gate)
-            U = _nystrom.lowrank_basis(gram, n_basis)
+            U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr)
         if k_zo_w is not None:
             uext_tail = -(U @ k_zo_w)
         Uext = U if uext_tail is None else torch.cat([U, uext_tail], 1)

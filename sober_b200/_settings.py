@@ -21,8 +21,8 @@ import contextlib
 import os
 
 _PRESETS = {
-    "parity": dict(gram="callable", gate="reference", nullspace="svd"),
-    "fast": dict(gram="cuda", gate="cholesky", nullspace="qr"),
+    "parity": dict(gram="callable", gate="reference", nullspace="svd", nystrom_qr="householder"),
+    "fast": dict(gram="cuda", gate="cholesky", nullspace="qr", nystrom_qr="cholqr2"),
 }
 
 

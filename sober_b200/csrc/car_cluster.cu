@@ -62,6 +62,11 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst_cluster, uint32_t src_cta,
                  "r"(src_cta), "r"(bytes), "r"(bar_cluster)
                  : "memory");
 }
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "d"(v), "r"(remote_bar)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Dynamic (CTA-uniform) row access into the register-resident column: a jump table, not RMAX selects.
@@ -267,6 +272,11 @@ __global__ void __launch_bounds__(CC_THREADS, 1) car_cluster_kernel(const CarClu
                      (uint32_t)(hi - lo) * 8u, map_rank(bar_addr[buf], t));
         }
     };
+    auto send_all = [&](int buf, const double* local_dst, double v) {   // per-element variant: same offset in every CTA
+        const uint32_t a = smem_addr(local_dst);
+#pragma unroll
+        for (int q = 0; q < P; ++q) st_async_f64(map_rank(a, q), v, map_rank(bar_addr[buf], q));
+    };
     auto wait_round = [&](int buf) {
         if (buf == 0) { mbar_wait(&bars[0], phase_bit0); phase_bit0 ^= 1; }
         else { mbar_wait(&bars[1], phase_bit1); phase_bit1 ^= 1; }
@@ -291,7 +301,11 @@ __global__ void __launch_bounds__(CC_THREADS, 1) car_cluster_kernel(const CarClu
             const bool own = (c % P == r);
             const double* piv = pc + (c & 1) * RMAX;           // column c of my rows, zero for rows <= c
             if (prof && c == 0) pr_t = clock64();
+#ifdef SOBER_CC_STASYNC
+            if (t == 0) mbar_expect_tx(&bars[buf], (uint32_t)(P + 1) * (uint32_t)(np - c) * 8u);
+#else
             if (t == 0) mbar_expect_tx(&bars[buf], (uint32_t)(P + 1) * (uint32_t)(W - lo) * 8u);
+#endif
             __syncthreads();   // pivot column c is in piv
             CC_TICK(0)
             if (t >= c && t < np) {
@@ -303,6 +317,12 @@ __global__ void __launch_bounds__(CC_THREADS, 1) car_cluster_kernel(const CarClu
                     s2 = fma(piv[li + 2], col[li + 2], s2);
                     s3 = fma(piv[li + 3], col[li + 3], s3);
                 }
+#ifdef SOBER_CC_STASYNC
+                send_all(buf, slot(buf, r) + t, (s0 + s1) + (s2 + s3));
+                if (own) send_all(buf, slot(buf, P) + t, col_get<RMAX>(col, lc));
+            }
+            CC_TICK(1)
+#else
                 stg(buf, 0)[t] = (s0 + s1) + (s2 + s3);
                 if (own) stg(buf, 1)[t] = col_get<RMAX>(col, lc);
             }
@@ -311,6 +331,7 @@ __global__ void __launch_bounds__(CC_THREADS, 1) car_cluster_kernel(const CarClu
             __syncthreads();
             push(buf, 0, r, lo, W);
             if (own) push(buf, 1, P, lo, W);
+#endif
             CC_TICK(2)
             wait_round(buf);
             CC_TICK(3)
@@ -360,7 +381,11 @@ __global__ void __launch_bounds__(CC_THREADS, 1) car_cluster_kernel(const CarClu
             ++round;
             const double ntc = -tau[c];
             if (prof && c == np - 1) pr_t = clock64();
+#ifdef SOBER_CC_STASYNC
+            if (t == 0) mbar_expect_tx(&bars[buf], (uint32_t)P * (uint32_t)k * 8u);
+#else
             if (t == 0) mbar_expect_tx(&bars[buf], (uint32_t)P * (uint32_t)W * 8u);
+#endif
             if (t < k) {
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
@@ -370,12 +395,18 @@ __global__ void __launch_bounds__(CC_THREADS, 1) car_cluster_kernel(const CarClu
                     s2 = fma(V[(size_t)(li + 2) * np + c], col[li + 2], s2);
                     s3 = fma(V[(size_t)(li + 3) * np + c], col[li + 3], s3);
                 }
+#ifdef SOBER_CC_STASYNC
+                send_all(buf, slot(buf, r) + t, (s0 + s1) + (s2 + s3));
+            }
+            CC_TICK(5)
+#else
                 stg(buf, 0)[t] = (s0 + s1) + (s2 + s3);
             }
             CC_TICK(5)
             fence_proxy_async_smem();
             __syncthreads();
             push(buf, 0, r, 0, W);
+#endif
             wait_round(buf);
             CC_TICK(6)
             if (t < k) {
@@ -425,17 +456,27 @@ __global__ void __launch_bounds__(CC_THREADS, 1) car_cluster_kernel(const CarClu
             }
             if (lane == 0) {
                 s_best = bi < 0 ? -1 : bi / P;
+#ifdef SOBER_CC_STASYNC
+                mbar_expect_tx(&bars[buf], (uint32_t)P * (uint32_t)(k - s + 2) * 8u);
+                send_all(buf, slot(buf, r) + W, br);
+                send_all(buf, slot(buf, r) + W + 1, (double)bi);
+#else
                 mbar_expect_tx(&bars[buf], (uint32_t)P * (uint32_t)(Wx - lo) * 8u);
                 stg(buf, 0)[W] = br;
                 stg(buf, 0)[W + 1] = (double)bi;
+#endif
             }
         }
         __syncthreads();
         CC_TICK(8)
+#ifdef SOBER_CC_STASYNC
+        if (t >= s && t < k) send_all(buf, slot(buf, r) + t, col_get<RMAX>(col, s_best));
+#else
         if (t >= s && t < k) stg(buf, 0)[t] = col_get<RMAX>(col, s_best);
         fence_proxy_async_smem();
         __syncthreads();
         push(buf, 0, r, lo, Wx);
+#endif
         CC_TICK(9)
         wait_round(buf);
         CC_TICK(10)
