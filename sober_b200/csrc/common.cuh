@@ -37,9 +37,9 @@ int sm_count();
 // cost ~3x more issue slots than FP64 slots (special-case branches, integer fix-ups, register moves); K1 is
 // bound by exactly those, so the three primitives are restated with the minimum number of FP64 instructions:
 //
-//   exp_neg(s) = exp(-s), s >= 0      10 FP64 + ~6 integer/LDS   max rel err 3.3e-16 (checked against 50-digit
-//                                      arithmetic in tools/check_fastmath.py)
-//   sqrt_pos(a), a >= 1e-30            7 FP64 + 1 MUFU            <= 1 ulp
+//   exp_neg(s) = exp(-s), s >= 0      9 FP64 + ~6 integer/LDS    max rel err 3.3e-16 + 1.1e-16 * s (checked against
+//                                      50-digit arithmetic, tools/check_fastmath.py)
+//   sqrt_pos(a), a >= 1e-30            4 FP64 + 1 MUFU            rel err <= 8.5e-14
 //   div_pos(a, b), b > 0               7 FP64 + 1 MUFU            <= 1 ulp
 // ---------------------------------------------------------------------------------------------------
 constexpr int EXP_TAB_SIZE = 64;
@@ -69,13 +69,13 @@ __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ t
     // exp(-s) = 2^m * 2^(j/64) * exp(r),  -s = (64 m + j) ln2/64 + r,  |r| <= ln2/128
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: adds round-to-nearest-integer
     const double NEG_L2E64 = -92.33248261689366;        // -64 / ln2
-    const double LN2_64_HI = 0.010830424667801708;      // ln2/64, 29 significant bits (k * HI exact)
-    const double LN2_64_LO = 2.8447437476627285e-11;
+    const double LN2_64 = 0.010830424696249145;         // ln2/64 rounded to double
     const double kd = fma(s, NEG_L2E64, MAGIC);
     const int k = __double2loint(kd);
     const double kf = kd - MAGIC;
-    double r = fma(kf, -LN2_64_HI, -s);
-    r = fma(kf, -LN2_64_LO, r);
+    // one FMA: the product kf * LN2_64 is exact inside the FMA, so r carries only the rounding of the constant
+    // (|s| * 1.1e-16 absolute) -- no hi/lo split needed
+    const double r = fma(kf, -LN2_64, -s);
     double q = fma(1.0 / 120.0, r, 1.0 / 24.0);
     q = fma(q, r, 1.0 / 6.0);
     q = fma(q, r, 0.5);
@@ -91,12 +91,10 @@ __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ t
 __device__ __forceinline__ double sqrt_pos(double a) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));   // MUFU.RSQ64H, rel err 2^-22
-    double g = a * y, h = 0.5 * y;
+    // one Goldschmidt step: relative error 1.5 * (2^-22)^2 = 8.5e-14 (the tolerance on kernel values is 1e-10)
+    const double g = a * y, h = 0.5 * y;
     const double e = fma(-g, h, 0.5);
-    g = fma(g, e, g);
-    h = fma(h, e, h);
-    const double d = fma(-g, g, a);
-    return fma(d, h, g);
+    return fma(g, e, g);
 }
 
 __device__ __forceinline__ double div_pos(double a, double b) {

@@ -67,10 +67,12 @@ def test_gram_matches_oracle(ops, cuda_device, name, variant):
             got_zx = rec._gram_T(rec._points(sub, spec, center, inv_ls), table).T
         finally:
             ops.variant = 0
+    # north_star tolerance: 1e-10 relative.  Measured: ~1e-12 (the 4-instruction sqrt of csrc/common.cuh carries a
+    # relative error of 1.3e-13, which enters exp(-r) multiplied by r)
     assert rel(got_zz, case.K_raw) < 1e-10
-    assert float((got_zz - case.K_raw).abs().max()) < 1e-12
+    assert float((got_zz - case.K_raw).abs().max()) < 1e-11
     want = kern(case.Z, sub)
-    assert float((got_zx - want).abs().max()) < 1e-12 and rel(got_zx, want) < 1e-10
+    assert float((got_zx - want).abs().max()) < 1e-11 and rel(got_zx, want) < 1e-10
 
 
 @pytest.mark.parametrize("nu", [0.5, 1.5])
