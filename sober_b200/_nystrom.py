@@ -54,17 +54,48 @@ def lowrank_basis(gram, rank, niter=2, qr="householder"):
     for _ in range(niter):
         q = _orthonormal_basis(gram.mH @ q, qr)
         q = _orthonormal_basis(gram @ q, qr)
-    small = q.mH @ gram                                   # (q x L)
+    small = q.mH @ gram                                   # B = Q^T K  (q x L)
     if qr == "cholqr2" and small.shape[0] <= small.shape[1]:
-        gs = small @ small.mH
-        chol, info = torch.linalg.cholesky_ex(gs)         # B^T = Q_B R with R = chol^H: only R is needed
-        if int(info) == 0:
-            # second pass for a numerically clean R:  B^T = Q1 R1, Q1 = Q2 R2  ->  R = R2 R1
-            q1t = torch.linalg.solve_triangular(chol, small, upper=False)          # Q1^T  (q x L)
-            chol2, info2 = torch.linalg.cholesky_ex(q1t @ q1t.mH)
-            if int(info2) == 0:
-                r_full = chol2.mH @ chol.mH                                          # upper triangular R
-                _, _, vh = torch.linalg.svd(r_full)
-                return -1 * (q @ vh.mH).T
-    u_small, _, _ = torch.linalg.svd(small, full_matrices=False)
+        u_small = _left_singular_vectors(small)
+    else:
+        u_small, _, _ = torch.linalg.svd(small, full_matrices=False)
     return -1 * (q @ u_small).T
+
+
+def _left_singular_vectors(b, max_sweeps=12, tol=1e-13):
+    """Left singular vectors of b (q x L, q <= L), descending, WITHOUT a Jacobi SVD (cuSOLVER gesvdj: 5 ms at
+    199 x 1000 and 100-200 ms at 999 x 2000 on B200 -- the largest N-independent item of the call).
+
+    1. eigh of the q x q Gram b b^T (1.9 / 12 ms): eigenvectors U0, accurate only to eps * cond(b)^2 / relgap.
+    2. First-order corrections that work on the FACTOR, like one-sided Jacobi does: with c = U^T b (rows nearly
+       orthogonal, norms ~ sigma_i) the entries g_ij = <c_i, c_j> carry an error eps * sigma_1 * sigma_j, so the
+       rotation angles x_ij = g_ij / (g_jj - g_ii) are accurate to eps * cond(b) / relgap -- the accuracy of the
+       Jacobi SVD itself.  U <- orth(U (I + X)): all pairs rotated at once with GEMMs, quadratically convergent once
+       the angles are small; repeated until max |x_ij| < tol (2-4 sweeps for cond(b) up to ~1e6).
+    Near-degenerate pairs (relative gap below 1e-9) are left alone: their individual vectors are ill-defined in the
+    reference as well.  If the iteration does not settle (cond(b)^2 beyond what eigh can seed), the Jacobi SVD of
+    torch.linalg.svd is used."""
+    gram = b @ b.mH
+    _, u = torch.linalg.eigh(gram)
+    u = u.flip(-1)                                        # descending, like svd
+    for _ in range(max_sweeps):
+        c = u.mH @ b
+        g = c @ c.mH
+        dg = torch.diagonal(g)
+        gap = dg.unsqueeze(0) - dg.unsqueeze(1)           # gap[i, j] = g_jj - g_ii
+        ok = gap.abs() > 1e-9 * (dg.unsqueeze(0) + dg.unsqueeze(1))
+        x = torch.where(ok, g / torch.where(ok, gap, torch.ones_like(gap)), torch.zeros_like(g))
+        x.diagonal().zero_()
+        size = x.abs().max()
+        x = x.clamp(-0.25, 0.25)
+        u = u + u @ x                                     # U (I + X), X skew-symmetric to first order
+        chol, info = torch.linalg.cholesky_ex(u.mH @ u)   # re-orthonormalise (one Cholesky-QR pass)
+        status = torch.stack([info.to(torch.float64).reshape(()), size.to(torch.float64).reshape(())]).tolist()
+        if status[0] != 0:
+            break
+        u = torch.linalg.solve_triangular(chol.mH, u, upper=True, left=False)
+        if status[1] < tol:
+            # order by the Rayleigh quotients actually reached (eigh's order can be off where it had no accuracy)
+            order = torch.argsort(torch.diagonal((u.mH @ b) @ (u.mH @ b).mH), descending=True)
+            return u[:, order]
+    return torch.linalg.svd(b, full_matrices=False)[0]

@@ -17,6 +17,8 @@ list, group = position mod S, exactly the reshape of SOBER/_rchq.py:118-123.  Wi
 enabled (``sober_b200.distributed``) candidates are row-sharded: each rank owns a contiguous range of positions
 and the only collective per iteration is one all-reduce of the (S x L') accumulator.
 """
+import time
+
 import torch
 
 from . import _car, _lib, _nystrom, _psd
@@ -87,6 +89,25 @@ class Alive:
 
     def tail(self, t0):
         return Alive(self.idx[t0:], self.mass[t0:], None if self.rec is None else self.rec[t0:])
+
+
+class _StageClock:
+    """Optional per-stage wall clock (``options.stats = {}``): synchronises the device at every stage boundary, so it
+    is a diagnostic, not something to leave on when timing the whole call."""
+
+    def __init__(self, sink, device):
+        self.sink, self.device, self.t = sink, device, None
+        if sink is not None and device.type == "cuda":
+            torch.cuda.synchronize(device)
+            self.t = time.perf_counter()
+
+    def lap(self, name):
+        if self.t is None:
+            return
+        torch.cuda.synchronize(self.device)
+        now = time.perf_counter()
+        self.sink[name] = self.sink.get(name, 0.0) + (now - self.t) * 1e3
+        self.t = now
 
 
 class Recombiner:
@@ -198,6 +219,7 @@ class Recombiner:
                 raise ValueError("init_weights must have shape (len(pts_rec),)")
             mu = ops.f64(init_weights)
 
+        clock = _StageClock(o.stats, dev)
         spec = introspect(kernel) if o.fuse else None
         if spec is not None and spec.d is not None and spec.d != X.shape[1]:
             raise ValueError("lengthscale dimension does not match the inputs")
@@ -212,7 +234,9 @@ class Recombiner:
             inv_ls = torch.ones(d, dtype=torch.float64, device=dev)
         records = self._use_records(spec, d)
 
+        clock.lap("setup")
         U, Uext, table = self._nystrom(Z, num_pts - 1, kernel, spec, center, inv_ls)
+        clock.lap("nystrom")
         n = U.shape[0]
         S = 2 * (n + 1)
         st = {"spec": spec, "table": table, "kernel": kernel, "X": X, "Z": Z,
@@ -224,15 +248,18 @@ class Recombiner:
         live = comm.all_gather_ints(n_local, dev)
         pos0, remaining = sum(live[:comm.rank]), sum(live)
         obj = None if calc_obj is None else (-1 * calc_obj(pts_rec.to(dev))).to(torch.float64)
+        clock.lap("compact+records")
 
         while True:
             if remaining <= S:
                 sel_idx, sel_w = self._finish(st, alive, n_local, pos0, remaining, n, UextT, row0, obj)
+                clock.lap("finish")
                 break
             E = remaining // S
             ES = E * S
             idx, mass = alive.idx, alive.mass
             at, totw = self._accumulate(st, alive, n_local, pos0, ES, S)
+            clock.lap("k1")
             Lp = at.shape[1]
             t0 = min(max(ES - pos0, 0), n_local)           # first local offset belonging to the remainder
             extra = torch.zeros(Lp + 3, dtype=torch.float64, device=dev)
@@ -265,7 +292,9 @@ class Recombiner:
                 self.trace("group", {"At": at.clone(), "totw": totw.clone(), "Xt_unnormalised": bary.clone(),
                                      "R": remaining, "E": E})
             bary = bary / totw.unsqueeze(1)
+            clock.lap("tail+project")
             wfull = _car.caratheodory(ops, bary, totw, o.nullspace, self.nullspace)
+            clock.lap("car")
             if obj is not None:
                 wfull = self._objective_step(bary[:, :n], bary[:, n], wfull)
             kept = wfull > 0
@@ -276,6 +305,7 @@ class Recombiner:
             alive = Alive(*ops.update_compact(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, keep.K,
                                               keep.tail_keep, new_pos0, new_local, rec=alive.rec, d=d))
             pos0, n_local, remaining = new_pos0, new_local, keep.before(remaining)
+            clock.lap("keepmap+update")
 
         # in-place sparse result in the caller's weight vector (SOBER/_rchq.py:109-110, 203-218)
         if init_weights is not None:
