@@ -141,13 +141,14 @@ int sober_group_accumulate_gram(const double* G, int64_t ldg, int32_t L, int64_t
  *   mu:    S weights, updated in place to the reduced measure (zeros at eliminated positions).
  *   pivots_out (k int32, may be NULL): eliminated position per step, -1 after an early stop.
  *   steps_out (1 int32, may be NULL): number of steps taken.
- * Arithmetic order is the reference's (unfused mul / div / sub), so given the same basis the pivots are
- * bit-identical.  Persistent cooperative kernel: sync_ws needs sober_car_workspace(k) bytes (zeroed by
- * the call).
+ * exact != 0: arithmetic order is the reference's (unfused mul / div / sub), so given the same basis the pivots
+ * are bit-identical.  exact == 0: one division per row (t_i = v_i / v_j) and an FMA per element (4x faster at
+ * S = 2000, differs from the reference only in rounding).  Persistent cooperative kernel: sync_ws needs
+ * sober_car_workspace(k) bytes (zeroed by the call).
  * ------------------------------------------------------------------------------------------------- */
 int64_t sober_car_workspace(int32_t k);
-int sober_car_eliminate(double* basis, int32_t k, int32_t S, double* mu, int32_t* pivots_out, int32_t* steps_out,
-                        void* sync_ws, int64_t sync_ws_bytes, void* stream);
+int sober_car_eliminate(double* basis, int32_t k, int32_t S, double* mu, int32_t exact, int32_t* pivots_out,
+                        int32_t* steps_out, void* sync_ws, int64_t sync_ws_bytes, void* stream);
 
 /* The whole Caratheodory reduction (SOBER/_rchq.py:224-270) in ONE kernel on one thread-block cluster, state
  * resident in distributed shared memory (sizes up to roughly S <= 440 on 8 CTAs, S <= 630 on 16):

@@ -38,8 +38,9 @@ def caratheodory(ops, feats, mass, how, nullspace=None):
         ops.car_cluster(out, design=design)
         return out
     rows = nullspace(design) if nullspace is not None else nullspace_rows(design, how)
+    exact = nullspace is not None or how != "qr"          # parity / injected bases keep the reference's rounding
     if fits is not None and fits(pts, dim, True):
-        ops.car_cluster(out, basis_rows=rows, exact=True)
+        ops.car_cluster(out, basis_rows=rows, exact=exact)
     else:
-        ops.car_eliminate(rows, out)
+        ops.car_eliminate(rows, out, exact=exact)
     return out

@@ -51,7 +51,7 @@ PROTOTYPES = {
     "sober_group_accumulate": (C.c_int, [C.POINTER(GroupArgs), _P, _I64, _P]),
     "sober_group_accumulate_gram": (C.c_int, [_P, _I64, _I32, _I64, _P, _I64, _I64, _I32, _P, _P, _P]),
     "sober_car_workspace": (_I64, [_I32]),
-    "sober_car_eliminate": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _I64, _P]),
+    "sober_car_eliminate": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P, _I64, _P]),
     "sober_car_cluster_fits": (C.c_int, [_I32, _I32, _I32]),
     "sober_car_cluster": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P, _P]),
     "sober_car_cluster_profiled": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P, _P, _P]),

@@ -78,7 +78,8 @@ def _left_singular_vectors(b, max_sweeps=12, tol=1e-13):
     gram = b @ b.mH
     _, u = torch.linalg.eigh(gram)
     u = u.flip(-1)                                        # descending, like svd
-    for _ in range(max_sweeps):
+    prev = float("inf")
+    for sweep in range(max_sweeps):
         c = u.mH @ b
         g = c @ c.mH
         dg = torch.diagonal(g)
@@ -94,7 +95,11 @@ def _left_singular_vectors(b, max_sweeps=12, tol=1e-13):
         if status[0] != 0:
             break
         u = torch.linalg.solve_triangular(chol.mH, u, upper=True, left=False)
-        if status[1] < tol:
+        # converged, or stagnated at the noise floor eps * cond(b) / relgap of the closest pair (clustered spectrum):
+        # the Jacobi SVD has the same intrinsic sensitivity there
+        stalled = sweep >= 2 and status[1] < 1e-5 and status[1] > 0.25 * prev
+        prev = status[1]
+        if status[1] < tol or stalled:
             # order by the Rayleigh quotients actually reached (eigh's order can be off where it had no accuracy)
             order = torch.argsort(torch.diagonal((u.mH @ b) @ (u.mH @ b).mH), descending=True)
             return u[:, order]

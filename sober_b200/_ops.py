@@ -184,7 +184,7 @@ class CudaOps:
         self.launches += 1
 
     # -- CAR -----------------------------------------------------------------------------------------------
-    def car_eliminate(self, basis_rows, mass, want_pivots=False):
+    def car_eliminate(self, basis_rows, mass, want_pivots=False, exact=True):
         """Runs the elimination in place on ``mass`` (S,); ``basis_rows`` (k x S, contiguous) is destroyed."""
         k, S = basis_rows.shape
         assert basis_rows.is_contiguous() and mass.is_contiguous()
@@ -194,7 +194,8 @@ class CudaOps:
         flags = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             t0 = self._begin("car_eliminate")
-            check(self.lib.sober_car_eliminate(_ptr(basis_rows), k, S, _ptr(mass), _ptr(piv), _ptr(steps), _ptr(flags),
+            check(self.lib.sober_car_eliminate(_ptr(basis_rows), k, S, _ptr(mass), int(bool(exact)), _ptr(piv), _ptr(steps),
+                                               _ptr(flags),
                                                flags.numel() * 4, self._stream()), "car_eliminate")
             self._end("car_eliminate", t0, k)                                   # work = elimination steps
         self.launches += 1

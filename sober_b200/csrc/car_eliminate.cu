@@ -39,9 +39,8 @@ __device__ __forceinline__ Best better(Best a, Best b) {
     return a;
 }
 
-constexpr int CAR_THREADS = 256;
 
-template <bool SMEM>
+template <bool SMEM, bool EXACT, int CAR_THREADS>
 __global__ void __launch_bounds__(CAR_THREADS) car_eliminate_kernel(double* __restrict__ basis, int k, int S,
                                                                     double* __restrict__ mu_g,
                                                                     int* __restrict__ pivots, int* __restrict__ steps,
@@ -100,7 +99,7 @@ __global__ void __launch_bounds__(CAR_THREADS) car_eliminate_kernel(double* __re
         if (t < 32) {
             Best r = t < CAR_THREADS / 32 ? red[t] : Best{0.0, -1};
 #pragma unroll
-            for (int off = 4; off > 0; off >>= 1) {
+            for (int off = 16; off > 0; off >>= 1) {
                 Best o;
                 o.ratio = __shfl_down_sync(0xffffffffu, r.ratio, off);
                 o.idx = __shfl_down_sync(0xffffffffu, r.idx, off);
@@ -113,13 +112,18 @@ __global__ void __launch_bounds__(CAR_THREADS) car_eliminate_kernel(double* __re
         if (piv.idx < 0) break;  // no positive entry: the guard of SOBER/_rchq.py:241-242
         const int j = piv.idx;
         const double vj = v_s[j];
+        if (!EXACT) __syncthreads();   // everybody holds v_j before v_s is overwritten with t_i below
         if (b == 0 && t == 0 && pivots) pivots[s] = j;
         done = s + 1;
 
         for (int i = t; i < S; i += CAR_THREADS) {
-            const double m = __dsub_rn(mu_s[i], __dmul_rn(piv.ratio, v_s[i]));
+            const double vi = v_s[i];
+            const double m = __dsub_rn(mu_s[i], __dmul_rn(piv.ratio, vi));
             mu_s[i] = (i == j) ? 0.0 : m;
+            // fast variant: one division per ROW (t_i = v_i / v_j) instead of one per matrix element
+            if (!EXACT) v_s[i] = __ddiv_rn(vi, vj);
         }
+        if (!EXACT) __syncthreads();
 
         // rank-1 update of the columns this CTA owns, the next pivot column first
         const int nxt = s + 1;
@@ -128,7 +132,8 @@ __global__ void __launch_bounds__(CAR_THREADS) car_eliminate_kernel(double* __re
             const double pj = col[j];
             __syncthreads();  // everyone has read col[j] before it is overwritten
             for (int i = t; i < S; i += CAR_THREADS) {
-                const double upd = __dsub_rn(col[i], __ddiv_rn(__dmul_rn(pj, v_s[i]), vj));
+                const double upd = EXACT ? __dsub_rn(col[i], __ddiv_rn(__dmul_rn(pj, v_s[i]), vj))
+                                         : fma(-pj, v_s[i], col[i]);
                 const double val = (i == j) ? 0.0 : upd;
                 col[i] = val;
                 if (SMEM) basis[(int64_t)nxt * S + i] = val;
@@ -144,7 +149,8 @@ __global__ void __launch_bounds__(CAR_THREADS) car_eliminate_kernel(double* __re
             const double pj = col[j];
             __syncthreads();
             for (int i = t; i < S; i += CAR_THREADS) {
-                const double upd = __dsub_rn(col[i], __ddiv_rn(__dmul_rn(pj, v_s[i]), vj));
+                const double upd = EXACT ? __dsub_rn(col[i], __ddiv_rn(__dmul_rn(pj, v_s[i]), vj))
+                                         : fma(-pj, v_s[i], col[i]);
                 col[i] = (i == j) ? 0.0 : upd;
             }
         }
@@ -167,7 +173,7 @@ using namespace sober;
 
 extern "C" int64_t sober_car_workspace(int32_t k) { return k > 0 ? (int64_t)k * 4 : 4; }
 
-extern "C" int sober_car_eliminate(double* basis, int32_t k, int32_t S, double* mu, int32_t* pivots_out,
+extern "C" int sober_car_eliminate(double* basis, int32_t k, int32_t S, double* mu, int32_t exact, int32_t* pivots_out,
                                    int32_t* steps_out, void* sync_ws, int64_t sync_ws_bytes, void* stream) {
     if (k < 0 || S <= 0 || !mu) return SOBER_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
@@ -195,15 +201,24 @@ extern "C" int sober_car_eliminate(double* basis, int32_t k, int32_t S, double* 
     if (!use_smem && smem_lite + 1024 > max_smem) return SOBER_ERR_UNSUPPORTED;
     const size_t smem = (size_t)(use_smem ? smem_full : smem_lite);
 
-    const void* fn = use_smem ? (const void*)car_eliminate_kernel<true> : (const void*)car_eliminate_kernel<false>;
+    // 1024 threads when the pivot search (S divisions per CTA per step) would otherwise dominate the step
+    const int threads = S > 768 ? 1024 : 256;
+    const void* fn;
+    if (threads == 1024) {
+        fn = use_smem ? (exact ? (const void*)car_eliminate_kernel<true, true, 1024> : (const void*)car_eliminate_kernel<true, false, 1024>)
+                      : (exact ? (const void*)car_eliminate_kernel<false, true, 1024> : (const void*)car_eliminate_kernel<false, false, 1024>);
+    } else {
+        fn = use_smem ? (exact ? (const void*)car_eliminate_kernel<true, true, 256> : (const void*)car_eliminate_kernel<true, false, 256>)
+                      : (exact ? (const void*)car_eliminate_kernel<false, true, 256> : (const void*)car_eliminate_kernel<false, false, 256>);
+    }
     SOBER_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    SOBER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, CAR_THREADS, smem));
+    SOBER_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
     if (per_sm < 1) return SOBER_ERR_UNSUPPORTED;
     if (G > per_sm * sms) G = per_sm * sms;  // cannot happen with G <= sms, kept as a guard
 
     int* flags = (int*)sync_ws;
     void* args[] = {&basis, &k, &S, &mu, &pivots_out, &steps_out, &flags};
-    SOBER_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(CAR_THREADS), args, smem, st));
+    SOBER_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(G), dim3(threads), args, smem, st));
     return SOBER_OK;
 }

@@ -96,7 +96,7 @@ class TorchOps:
             inside = pos < ES
             totw.index_add_(0, (pos % S)[inside], w[inside])
 
-    def car_eliminate(self, basis_rows, mass, want_pivots=False):
+    def car_eliminate(self, basis_rows, mass, want_pivots=False, exact=True):
         removed = oracle.eliminate(basis_rows.T.clone(), mass, oracle.Factory())
         if want_pivots:
             k = basis_rows.shape[0]
