@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsober_b200.so")
+# SOBER_B200_LIB: alternative build of the same ABI (kernel-variant experiments, see tools/k1_variants.sh)
+LIB_PATH = os.environ.get("SOBER_B200_LIB") or os.path.join(_HERE, "libsober_b200.so")
 
 OK = 0
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "unsupported shape/family", 4: "workspace too small"}

@@ -42,6 +42,8 @@ int sm_count();
 //   sqrt_pos(a), a >= 1e-30            4 FP64 + 1 MUFU            rel err <= 8.5e-14
 //   div_pos(a, b), b > 0               7 FP64 + 1 MUFU            <= 1 ulp
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 constexpr int EXP_TAB_SIZE = 64;
 static __device__ const double EXP2_TAB[EXP_TAB_SIZE] = {  // 2^(j/64), correctly rounded (50-digit source)
     1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
@@ -65,11 +67,22 @@ __device__ __forceinline__ void load_exp_table(double* tab_smem, int tid, int nt
     for (int j = tid; j < EXP_TAB_SIZE; j += nthreads) tab_smem[j] = EXP2_TAB[j];
 }
 
-__device__ __forceinline__ double exp_neg(double s, const double* __restrict__ tab) {
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+    return v;
+}
+
+// `tab` is the SHARED-SPACE address of the 64-entry table (smem_addr(tab_smem)): a generic pointer would cost a
+// generic->shared conversion (S2UR SR_CgaCtaId + ULEA) at every use
+__device__ __forceinline__ double exp_neg(double s_in, uint32_t tab) {
     // exp(-s) = 2^m * 2^(j/64) * exp(r),  -s = (64 m + j) ln2/64 + r,  |r| <= ln2/128
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: adds round-to-nearest-integer
     const double NEG_L2E64 = -92.33248261689366;        // -64 / ln2
     const double LN2_64 = 0.010830424696249145;         // ln2/64 rounded to double
+    // clamp s at ~700 through the integer pipe (s >= 0: high words order like ints): below 1e-304 the exponent
+    // trick at the end would wrap
+    const double s = __hiloint2double(min(__double2hiint(s_in), 0x4085E000), __double2loint(s_in));
     const double kd = fma(s, NEG_L2E64, MAGIC);
     const int k = __double2loint(kd);
     const double kf = kd - MAGIC;
@@ -81,11 +94,10 @@ __device__ __forceinline__ double exp_neg(double s, const double* __restrict__ t
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     const double p = fma(q, r, 1.0);
-    const double v = tab[k & (EXP_TAB_SIZE - 1)] * p;   // in [1, 2)
-    const int hi = __double2hiint(v) + ((k >> 6) << 20);  // scale by 2^m on the exponent field (ALU pipe)
-    const double res = __hiloint2double(hi, __double2loint(v));
-    // below 1e-304: flush (the exponent trick would wrap); integer compare on the high word keeps it off the FP64 pipe
-    return __double2hiint(s) > 0x4085E000 ? 0.0 : res;   // s > 700
+    const double v = lds_f64(tab + ((k & (EXP_TAB_SIZE - 1)) << 3)) * p;   // in [1, 2)
+    // scale by 2^m on the exponent field (ALU pipe): hi += (k >> 6) << 20 == (k & ~63) << 14
+    const int hi = __double2hiint(v) + ((k & ~(EXP_TAB_SIZE - 1)) << 14);
+    return __hiloint2double(hi, __double2loint(v));
 }
 
 __device__ __forceinline__ double sqrt_pos(double a) {
@@ -123,7 +135,7 @@ __device__ __forceinline__ double clamp_min_pos(double a, double floor_) {
 // with r = sqrt(d2).  The output scale is applied once per output entry by the caller (linearity).
 // ---------------------------------------------------------------------------------------------------
 template <int FAM>
-__device__ __forceinline__ double stationary_value(double d2, const double* __restrict__ tab) {
+__device__ __forceinline__ double stationary_value(double d2, uint32_t tab) {
     if (FAM == SOBER_RBF) {
         return exp_neg(clamp_min_pos(d2, 0.0), tab);
     }
@@ -142,7 +154,7 @@ __device__ __forceinline__ double tanimoto_value(double dot, double xn, double z
 }
 
 template <int FAM>
-__device__ __forceinline__ double kernel_value(double dot, double xn, double zn, const double* __restrict__ tab) {
+__device__ __forceinline__ double kernel_value(double dot, double xn, double zn, uint32_t tab) {
     if (FAM == SOBER_TANIMOTO) return tanimoto_value(dot, xn, zn);
     return stationary_value<FAM>((xn + zn) + dot, tab);
 }
@@ -150,7 +162,6 @@ __device__ __forceinline__ double kernel_value(double dot, double xn, double zn,
 // ---------------------------------------------------------------------------------------------------
 // TMA 1-D bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));

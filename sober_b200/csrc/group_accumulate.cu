@@ -7,7 +7,7 @@
 //
 // Two kernels share one contract:
 //   * group_records : d <= 8, record layout.  A CTA owns TG adjacent groups and up to 8*32*TL landmarks (one lane
-//                     = TL landmarks held in registers).  The candidate records of its rows are staged into
+//                     = TL landmarks held in registers; TL = 2, TG = 4 measured best of 8 variants, tools/k1_variants.sh).  The candidate records of its rows are staged into
 //                     shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier, 3 stages) issued by one
 //                     thread; every warp then reads each record as a broadcast LDS and evaluates TL x TG kernel
 //                     values.  FP64-pipe bound: ~28 FP64 instructions per Matern-5/2 evaluation (common.cuh).
@@ -46,8 +46,11 @@ constexpr int REC_THREADS = REC_WARPS * 32;
 constexpr int REC_ROWS = 16;    // rows per pipeline stage
 constexpr int REC_STAGES = 3;
 
+#ifndef SOBER_REC_MINB
+#define SOBER_REC_MINB 2
+#endif
 template <int D, int FAM, int TL, int TG>
-__global__ void __launch_bounds__(REC_THREADS) group_records_kernel(const GroupParams p) {
+__global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_kernel(const GroupParams p) {
     constexpr int LDR = (D + 3) / 2 * 2;  // d + 2 rounded up to even
     __shared__ __align__(16) double buf[REC_STAGES][REC_ROWS][TG][LDR];
     __shared__ __align__(8) uint64_t bars[REC_STAGES];
@@ -60,6 +63,7 @@ __global__ void __launch_bounds__(REC_THREADS) group_records_kernel(const GroupP
     const bool active = l0 < p.L;
 
     load_exp_table(tab, t, REC_THREADS);
+    const uint32_t tab_s = smem_addr(tab);
     if (t == 0) {
         for (int s = 0; s < REC_STAGES; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
@@ -126,6 +130,17 @@ __global__ void __launch_bounds__(REC_THREADS) group_records_kernel(const GroupP
         mbar_wait(&bars[stage], (uint32_t)((c / REC_STAGES) & 1));
         const int64_t e0 = r0 + (int64_t)c * REC_ROWS;
         const int nrows = (int)min((int64_t)REC_ROWS, r1 - e0);
+        if (count_tw) {
+            // group weight totals (positions below ES only): one thread, kept out of the FP64-critical loop below
+            for (int r = 0; r < nrows; ++r) {
+                int ja, jb;
+                interval(e0 + r, ja, jb);
+#pragma unroll
+                for (int j = 0; j < TG; ++j)
+                    if (j >= ja && j < jb && (e0 + r) * p.S + g0 + j < p.ES)
+                        tw[j] += p.unit_weights ? 1.0 : buf[stage][r][j][D + 1];
+            }
+        }
         if (active) {
             for (int r = 0; r < nrows; ++r) {
                 int ja, jb;
@@ -150,16 +165,12 @@ __global__ void __launch_bounds__(REC_THREADS) group_records_kernel(const GroupP
 #pragma unroll
                             for (int k = 0; k < D; ++k) dot = fma(x[j][k], zt[i][k], dot);
                             val[i][j] = (FAM == SOBER_TANIMOTO) ? tanimoto_value(dot, xn[j], zn[i])
-                                                                : stationary_value<FAM>(xn[j] + dot, tab);
+                                                                : stationary_value<FAM>(xn[j] + dot, tab_s);
                         }
 #pragma unroll
                     for (int i = 0; i < TL; ++i)
 #pragma unroll
                         for (int j = 0; j < TG; ++j) acc[i][j] = fma(val[i][j], w[j], acc[i][j]);
-                    if (count_tw && (e0 + r) * p.S + g0 < p.ES) {
-#pragma unroll
-                        for (int j = 0; j < TG; ++j) tw[j] += w[j];
-                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < TG; ++j) {
@@ -173,10 +184,9 @@ __global__ void __launch_bounds__(REC_THREADS) group_records_kernel(const GroupP
 #pragma unroll
                             for (int k = 0; k < D; ++k) dot = fma(rp[k], zt[i][k], dot);
                             const double v = (FAM == SOBER_TANIMOTO) ? tanimoto_value(dot, xn, zn[i])
-                                                                     : stationary_value<FAM>(xn + dot, tab);
+                                                                     : stationary_value<FAM>(xn + dot, tab_s);
                             acc[i][j] = fma(v, w, acc[i][j]);
                         }
-                        if (count_tw && (e0 + r) * p.S + g0 + j < p.ES) tw[j] += w;
                     }
                 }
             }
@@ -220,6 +230,7 @@ __global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
     const int g0 = blockIdx.x * TN;
     const int l0 = blockIdx.y * TM;
     load_exp_table(tab, t, 256);
+    const uint32_t tab_s = smem_addr(tab);
 
     double zn[4];
 #pragma unroll
@@ -298,7 +309,7 @@ __global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
             const double xn = s_xn[tx + 16 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double kv = kernel_value<FAM>(dot[i][j], xn, zn[i], tab);
+                const double kv = kernel_value<FAM>(dot[i][j], xn, zn[i], tab_s);
                 acc[i][j] = fma(kv, w, acc[i][j]);
             }
         }
@@ -360,8 +371,14 @@ __global__ void group_gram_kernel(const double* __restrict__ G, int64_t ldg, int
 // -------------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------------
-constexpr int REC_TL = 4;
-constexpr int REC_TG = 2;
+#ifndef SOBER_REC_TL
+#define SOBER_REC_TL 2
+#endif
+#ifndef SOBER_REC_TG
+#define SOBER_REC_TG 4
+#endif
+constexpr int REC_TL = SOBER_REC_TL;   // landmarks per lane
+constexpr int REC_TG = SOBER_REC_TG;   // groups per CTA
 
 struct Plan {
     bool records;
