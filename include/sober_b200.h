@@ -37,7 +37,8 @@ enum sober_family {
     SOBER_MATERN12 = 1, /* exp(-r)                                     r  = sqrt(max(d2,1e-30))           */
     SOBER_MATERN32 = 2, /* (1+sqrt3 r) exp(-sqrt3 r)                                                      */
     SOBER_MATERN52 = 3, /* (1+sqrt5 r+5/3 r^2) exp(-sqrt5 r)                                              */
-    SOBER_TANIMOTO = 4  /* max(0,(<x,z>+1e-6)/(1e-6+|x|^2+|z|^2-<x,z>))                                   */
+    SOBER_TANIMOTO = 4, /* max(0,(<x,z>+1e-6)/(1e-6+|x|^2+|z|^2-<x,z>))                                   */
+    SOBER_TANIMOTO_BITS = 5 /* the same on bit-packed {0,1} rows: <x,z> = popcount(x & z)  (sober_pack_bits)  */
 };
 
 int sober_abi_version(void);
@@ -63,6 +64,14 @@ int sober_prepare_points(const double* X, int64_t ldx, int64_t n, int32_t d, con
  * norm of gpytorch's distance (SOBER/_rchq.py:124 -> covar_module.forward). */
 int sober_make_records(const double* X, int64_t ldx, int32_t d, const double* center, const double* inv_ls,
                        const int32_t* idx, const double* mu, int64_t m, double* rec, int64_t ldr, void* stream);
+
+/* Bit-packing of {0,1}-valued rows (fingerprints, SOBER/_drug_modelling.py; the reference stores them as floats):
+ * words[i, w] bit b = (X[i, 64 w + b] != 0), ldw >= ceil(d / 64) words per row (padding words zeroed; K1 wants ldw in
+ * {1,2,4,8,16,32}); popc[i] = number of set bits (= |x|^2);
+ * *not_binary (device int32, must be zeroed by the caller) is set to 1 if any entry is neither 0 nor 1.
+ * One streaming pass over X; afterwards family SOBER_TANIMOTO_BITS evaluates <x,z> as popcount(x & z). */
+int sober_pack_bits(const double* X, int64_t ldx, int64_t n, int32_t d, uint64_t* words, int32_t ldw, double* popc,
+                    int32_t* not_binary, void* stream);
 
 /* out[i] = sum_k X[i,k]^2  (Tanimoto |x|^2, SOBER/_drug_modelling.py:21-22). */
 int sober_row_sqnorm(const double* X, int64_t ldx, int64_t n, int32_t d, double* out, void* stream);
@@ -94,6 +103,8 @@ int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_out, double*
  * Stationary families expect coordinates pre-multiplied by the family constant (1/sqrt2 RBF, 1 Matern-1/2,
  * sqrt3 Matern-3/2, sqrt5 Matern-5/2): fold it into inv_ls.
  * Zt (L x d): landmark table -- stationary: -2 (z - c) * inv_ls ; Tanimoto: z.   zn (L): |.|^2 of the same.
+ * SOBER_TANIMOTO_BITS (indexed layout only): X and Zt point to uint64 word rows from sober_pack_bits (ldx = words per
+ *   row, d = number of BITS, a multiple-of-64 padded row), xn / zn are the popcounts as doubles.
  * At: S x L (transposed on purpose: coalesced stores and it is the left operand of the projection).
  * workspace holds the per-split partial sums (deterministic two-stage reduction, no atomics).
  * variant: 0 = automatic (records -> register kernel, else tiled), 1 = force the generic tiled kernel.

@@ -14,9 +14,10 @@ LIB_PATH = os.environ.get("SOBER_B200_LIB") or os.path.join(_HERE, "libsober_b20
 OK = 0
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "unsupported shape/family", 4: "workspace too small"}
 
-RBF, MATERN12, MATERN32, MATERN52, TANIMOTO = range(5)
+RBF, MATERN12, MATERN32, MATERN52, TANIMOTO, TANIMOTO_BITS = range(6)
 # constant folded into the lengthscale so that the kernels see  RBF = exp(-d2), Matern = f(r), r = sqrt(d2)
 FAMILY_SCALE = {RBF: 0.5 ** 0.5, MATERN12: 1.0, MATERN32: 3.0 ** 0.5, MATERN52: 5.0 ** 0.5, TANIMOTO: 1.0}
+BITS_MAX_D = 2048  # the popcount Tanimoto kernel covers fingerprints of up to 2048 bits
 RECORD_MAX_D = 8   # the register kernel of K1 (record layout) covers d <= 8
 
 
@@ -45,6 +46,7 @@ PROTOTYPES = {
     "sober_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
     "sober_prepare_points": (C.c_int, [_P, _I64, _I64, _I32, _P, _P, _P, _I64, _P]),
     "sober_make_records": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _P, _I64, _P, _I64, _P]),
+    "sober_pack_bits": (C.c_int, [_P, _I64, _I64, _I32, _P, _I32, _P, _P, _P]),
     "sober_row_sqnorm": (C.c_int, [_P, _I64, _I64, _I32, _P, _P]),
     "sober_compact_workspace": (_I64, [_I64]),
     "sober_compact_nonzero": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I64, _P]),

@@ -35,11 +35,13 @@ def record_stride(d):
 
 
 class LandmarkTable:
-    """``Zt`` (L x d) and ``zn`` (L) as K1 wants them, plus the family / output scale."""
+    """``Zt`` (L x d) and ``zn`` (L) as K1 wants them, plus the family / output scale.  ``d`` overrides the column
+    count when the rows are bit-packed words (family TANIMOTO_BITS: d = number of bits)."""
 
-    def __init__(self, zt, zn, family, outputscale):
+    def __init__(self, zt, zn, family, outputscale, d=None):
         self.zt, self.zn, self.family, self.outputscale = zt, zn, family, float(outputscale)
-        self.L, self.d = zt.shape
+        self.L = zt.shape[0]
+        self.d = zt.shape[1] if d is None else int(d)
 
 
 class CudaOps:
@@ -114,6 +116,24 @@ class CudaOps:
             self._end("make_records", t0, 8 * m * (d + 2 + ldr))
         self.launches += 1
         return PointSet(None, 0, None, 0, m, d, rec=rec, ldr=ldr)
+
+    def pack_bits(self, X):
+        """{0,1}-valued rows -> (words (n x W int64), popcounts (n,), all_binary: bool).  One streaming pass and one
+        host sync (the flag).  W = ceil(d / 64) rounded up to a power of two (what the popcount kernel takes)."""
+        n, d = X.shape
+        W = 1
+        while W * 64 < d:
+            W *= 2
+        words = torch.empty((n, W), dtype=torch.int64, device=self.device)
+        popc = torch.empty(n, dtype=torch.float64, device=self.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            t0 = self._begin("pack_bits")
+            check(self.lib.sober_pack_bits(_ptr(X), X.stride(0), n, d, _ptr(words), W, _ptr(popc), _ptr(flag),
+                                           self._stream()), "pack_bits")
+            self._end("pack_bits", t0, 8 * n * (d + W + 1))
+        self.launches += 1
+        return words, popc, int(flag.item()) == 0
 
     def raw_points(self, X):
         """Tanimoto layout: the rows as they are plus |x|^2."""

@@ -23,7 +23,7 @@ import torch
 
 from . import _car, _lib, _nystrom, _psd
 from ._kernel_spec import introspect
-from ._ops import LandmarkTable
+from ._ops import LandmarkTable, PointSet
 from ._settings import options
 
 
@@ -118,12 +118,18 @@ class Recombiner:
         self.nullspace = nullspace        # test hook: design -> (k x S) rows
         self.basis = basis                # test hook: use this Nystrom basis U (n x L) instead of computing it
         self.trace = trace                # test hook: trace(stage, dict) with per-iteration intermediates
+        self._bits = False                # set per call: Tanimoto on {0,1} rows -> bit-packed popcount kernel
 
     # -----------------------------------------------------------------------------------------------------
     # landmarks / Nystrom block
     # -----------------------------------------------------------------------------------------------------
     def _table(self, pts, spec, center, inv_ls):
         """LandmarkTable for raw landmark rows ``pts`` (L' x d)."""
+        if self._bits:
+            words, popc, ok = self.ops.pack_bits(pts)
+            if not ok:
+                raise ValueError("non-binary landmark rows on the bit-packed Tanimoto path")
+            return LandmarkTable(words, popc, _lib.TANIMOTO_BITS, spec.outputscale, d=pts.shape[1])
         if spec.stationary:
             v = (pts - center) * inv_ls
             return LandmarkTable((-2.0 * v).contiguous(), (v * v).sum(-1).contiguous(), spec.family, spec.outputscale)
@@ -133,6 +139,11 @@ class Recombiner:
         return spec is not None and d <= _lib.RECORD_MAX_D and self.opts.k1_variant != 1
 
     def _points(self, X, spec, center, inv_ls):
+        if self._bits:
+            words, popc, ok = self.ops.pack_bits(X)
+            if not ok:
+                raise ValueError("non-binary rows on the bit-packed Tanimoto path")
+            return PointSet(words, words.stride(0), popc, 1, X.shape[0], X.shape[1])
         if self._use_records(spec, X.shape[1]):
             return self.ops.make_records(X, center, inv_ls)
         return self.ops.prepare_points(X, center, inv_ls) if spec.stationary else self.ops.raw_points(X)
@@ -232,7 +243,20 @@ class Recombiner:
         elif spec is not None:
             center = torch.zeros(d, dtype=torch.float64, device=dev)
             inv_ls = torch.ones(d, dtype=torch.float64, device=dev)
-        records = self._use_records(spec, d)
+        # Tanimoto on fingerprints: if every entry of the candidates and landmarks is 0/1 the rows are bit-packed once
+        # and <x, z> becomes popcount(x & z)  (64x less data, integer pipe instead of d FP64 FMAs per pair)
+        self._bits = False
+        cand_bits = None
+        if (spec is not None and spec.family == _lib.TANIMOTO and _lib.RECORD_MAX_D < d <= _lib.BITS_MAX_D
+                and o.k1_variant != 1 and hasattr(ops, "pack_bits")):
+            zw, zp, z_ok = ops.pack_bits(Z)
+            if z_ok and (spec.x_obs is None or ops.pack_bits(ops.f64(spec.x_obs))[2]):
+                xw, xp, x_ok = ops.pack_bits(X)
+                flags = comm.all_gather_ints(int(x_ok), dev)
+                if all(flags):
+                    self._bits = True
+                    cand_bits = PointSet(xw, xw.stride(0), xp, 1, X.shape[0], d)
+        records = self._use_records(spec, d) and not self._bits
 
         clock.lap("setup")
         U, Uext, table = self._nystrom(Z, num_pts - 1, kernel, spec, center, inv_ls)
@@ -240,7 +264,8 @@ class Recombiner:
         n = U.shape[0]
         S = 2 * (n + 1)
         st = {"spec": spec, "table": table, "kernel": kernel, "X": X, "Z": Z,
-              "pts": self._points(X, spec, center, inv_ls) if (spec is not None and not records) else None}
+              "pts": (cand_bits if cand_bits is not None else self._points(X, spec, center, inv_ls))
+              if (spec is not None and not records) else None}
         UextT = Uext.T.contiguous()
 
         idx, mass, n_local = ops.compact_nonzero(mu)

@@ -330,6 +330,135 @@ __global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
     if (blockIdx.y == 0 && t < TN && g0 + t < p.S) p.totw_out[(int64_t)blockIdx.z * p.S + g0 + t] = tw;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Tanimoto on bit-packed fingerprints: <x, z> = popcount(x & z)   (indexed layout)
+// -------------------------------------------------------------------------------------------------
+// A lane holds TL landmarks' bit rows in registers (W 64-bit words each); a CTA (8 warps) covers 256 * TL landmarks
+// and TG groups.  Candidate bit rows of a chunk of rows are staged into shared memory with 16-byte loads and read
+// back as broadcast LDS.  Per pair: W x (AND + POPC) on the integer pipe, then the FP64 Tanimoto ratio (one
+// division = 7 FP64 instructions) and the weighted accumulate.  d = 1024: 16 words -> ~70 integer + 12 FP64
+// instructions per pair instead of 1024 DFMAs.
+constexpr int BITS_ROWS = 8;   // rows per staged chunk
+
+template <int W, int TL, int TG>
+__global__ void __launch_bounds__(256) group_bits_kernel(const GroupParams p) {
+    __shared__ __align__(16) uint64_t xb[BITS_ROWS][TG][W];
+    __shared__ double s_w[BITS_ROWS][TG], s_xn[BITS_ROWS][TG];
+    __shared__ int64_t s_row[BITS_ROWS][TG];
+
+    const uint64_t* __restrict__ Xw = reinterpret_cast<const uint64_t*>(p.X);
+    const uint64_t* __restrict__ Zw = reinterpret_cast<const uint64_t*>(p.Zt);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int g0 = blockIdx.x * TG;
+    const int l0 = (blockIdx.y * 8 + warp) * (32 * TL);
+    const bool active = l0 < p.L;
+
+    uint64_t zb[TL][W];
+    double zn[TL];
+#pragma unroll
+    for (int i = 0; i < TL; ++i) {
+        const int l = l0 + lane + 32 * i;
+        const bool ok = l < p.L;
+#pragma unroll
+        for (int w = 0; w < W; ++w) zb[i][w] = ok ? __ldg(Zw + (int64_t)l * W + w) : 0ull;
+        zn[i] = ok ? __ldg(p.zn + l) : 0.0;
+    }
+    double acc[TL][TG], tw[TG];
+#pragma unroll
+    for (int j = 0; j < TG; ++j) {
+        tw[j] = 0.0;
+#pragma unroll
+        for (int i = 0; i < TL; ++i) acc[i][j] = 0.0;
+    }
+    const int64_t r0 = p.row_begin + (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t r1 = min(p.row_end, r0 + p.rows_per_split);
+    const int64_t hi = p.pos0 + p.n_local;
+    const bool count_tw = (blockIdx.y == 0) && (t == 0);
+    constexpr int CHUNK = BITS_ROWS * TG;
+    constexpr int VEC_PER_ROW = W / 2 > 0 ? W / 2 : 1;   // 16-byte vectors per bit row (W even) -- W == 1 handled below
+
+    for (int64_t e0 = r0; e0 < r1; e0 += BITS_ROWS) {
+        __syncthreads();   // previous chunk fully consumed
+        if (t < CHUNK) {
+            const int r = t / TG, j = t % TG;
+            const int g = g0 + j;
+            const int64_t e = e0 + r;
+            const int64_t pos = e * p.S + g;
+            const bool ok = (e < r1) && (g < p.S) && (pos >= p.pos0) && (pos < hi);
+            int64_t row = -1;
+            double w = 0.0, xn = 0.0;
+            if (ok) {
+                const int64_t loc = pos - p.pos0;
+                row = p.idx ? (int64_t)__ldg(p.idx + loc) : loc;
+                w = p.mu ? __ldg(p.mu + loc) : 1.0;
+                xn = __ldg(p.xn + row * p.xn_stride);
+            }
+            s_row[r][j] = row;
+            s_w[r][j] = w;
+            s_xn[r][j] = xn;
+        }
+        __syncthreads();
+        if (W >= 2) {
+            for (int v = t; v < CHUNK * VEC_PER_ROW; v += 256) {
+                const int c = v / VEC_PER_ROW, q = v % VEC_PER_ROW;
+                const int64_t row = s_row[c / TG][c % TG];
+                uint4 val = make_uint4(0, 0, 0, 0);
+                if (row >= 0) val = __ldg(reinterpret_cast<const uint4*>(Xw + row * p.ldx) + q);
+                reinterpret_cast<uint4*>(&xb[c / TG][c % TG][0])[q] = val;
+            }
+        } else {
+            for (int c = t; c < CHUNK; c += 256) {
+                const int64_t row = s_row[c / TG][c % TG];
+                xb[c / TG][c % TG][0] = row >= 0 ? __ldg(Xw + row * p.ldx) : 0ull;
+            }
+        }
+        __syncthreads();
+        if (count_tw) {
+            for (int r = 0; r < BITS_ROWS; ++r)
+#pragma unroll
+                for (int j = 0; j < TG; ++j)
+                    if (s_row[r][j] >= 0 && (e0 + r) * p.S + g0 + j < p.ES) tw[j] += s_w[r][j];
+        }
+        if (active) {
+            const int nrows = (int)min((int64_t)BITS_ROWS, r1 - e0);
+            for (int r = 0; r < nrows; ++r) {
+#pragma unroll
+                for (int j = 0; j < TG; ++j) {
+                    if (s_row[r][j] < 0) continue;     // warp-uniform
+                    int cnt[TL];
+#pragma unroll
+                    for (int i = 0; i < TL; ++i) cnt[i] = 0;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        const uint64_t xw = xb[r][j][w];
+#pragma unroll
+                        for (int i = 0; i < TL; ++i) cnt[i] += __popcll(xw & zb[i][w]);
+                    }
+                    const double xn = s_xn[r][j], wgt = s_w[r][j];
+#pragma unroll
+                    for (int i = 0; i < TL; ++i) {
+                        const double kv = tanimoto_value((double)cnt[i], xn, zn[i]);
+                        acc[i][j] = fma(kv, wgt, acc[i][j]);
+                    }
+                }
+            }
+        }
+    }
+
+    double* out = p.out + (int64_t)blockIdx.z * p.S * p.L;
+#pragma unroll
+    for (int j = 0; j < TG; ++j) {
+        const int g = g0 + j;
+        if (g >= p.S) continue;
+#pragma unroll
+        for (int i = 0; i < TL; ++i) {
+            const int l = l0 + lane + 32 * i;
+            if (l < p.L) out[(int64_t)g * p.L + l] = acc[i][j] * p.scale;
+        }
+        if (count_tw) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw[j];
+    }
+}
+
 // fixed-order reduction of the row-splits; applies the output scale
 __global__ void reduce_splits_kernel(const double* __restrict__ part, const double* __restrict__ tw_part,
                                      int nsplit, int64_t SL, int S, double scale, double* __restrict__ At,
@@ -380,8 +509,12 @@ __global__ void group_gram_kernel(const double* __restrict__ G, int64_t ldg, int
 constexpr int REC_TL = SOBER_REC_TL;   // landmarks per lane
 constexpr int REC_TG = SOBER_REC_TG;   // groups per CTA
 
+constexpr int BITS_TG = 4;
+static int bits_tl(int W) { return W <= 8 ? 4 : (W <= 16 ? 2 : 1); }
+
 struct Plan {
     bool records;
+    bool bits;
     dim3 grid, block;
     int nsplit;
     int64_t rows_per_split, row_begin, row_end;
@@ -394,9 +527,20 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
     pl->row_end = a->n_local > 0 ? ceil_div(hi, a->S) : pl->row_begin;
     const int64_t rows = pl->row_end - pl->row_begin;
     pl->records = a->rec != nullptr && a->variant != 1;
+    pl->bits = a->family == SOBER_TANIMOTO_BITS;
+    if (pl->bits) {
+        const int64_t W = a->ldx;
+        if (pl->records || a->d <= 0 || W < (a->d + 63) / 64 || !(W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32))
+            return false;
+    }
     if (pl->records && (a->d > 8 || a->ldr != (a->d + 3) / 2 * 2)) return false;
     int64_t gx, gy, target;
-    if (pl->records) {
+    if (pl->bits) {
+        gx = ceil_div(a->S, BITS_TG);
+        gy = ceil_div(a->L, 8 * 32 * bits_tl((int)a->ldx));
+        pl->block = dim3(256);
+        target = (int64_t)sm_count() * 12;
+    } else if (pl->records) {
         gx = ceil_div(a->S, REC_TG);
         gy = ceil_div(a->L, REC_WARPS * 32 * REC_TL);
         pl->block = dim3(REC_THREADS);
@@ -437,6 +581,18 @@ static bool launch_records_d(const Plan& pl, const GroupParams& p, cudaStream_t 
     }
 }
 
+static bool launch_bits(const Plan& pl, const GroupParams& p, cudaStream_t st) {
+    switch ((int)p.ldx) {
+        case 1: group_bits_kernel<1, 4, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
+        case 2: group_bits_kernel<2, 4, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
+        case 4: group_bits_kernel<4, 4, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
+        case 8: group_bits_kernel<8, 4, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
+        case 16: group_bits_kernel<16, 2, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
+        case 32: group_bits_kernel<32, 1, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
+        default: return false;
+    }
+}
+
 template <int FAM>
 static bool launch_family(const Plan& pl, const GroupParams& p, cudaStream_t st) {
     if (pl.records) return launch_records_d<FAM>(pl, p, st);
@@ -461,7 +617,7 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
     if (!plan_group(a, &pl)) return SOBER_ERR_ARG;
     if (!a->Zt || !a->zn || !a->At || !a->totw) return SOBER_ERR_ARG;
     if (!pl.records && (!a->X || !a->xn)) return SOBER_ERR_ARG;
-    if (a->family < SOBER_RBF || a->family > SOBER_TANIMOTO) return SOBER_ERR_UNSUPPORTED;
+    if (a->family < SOBER_RBF || a->family > SOBER_TANIMOTO_BITS) return SOBER_ERR_UNSUPPORTED;
     const int64_t need = sober_group_accumulate_workspace(a);
     if (need > workspace_bytes || (need > 0 && !workspace)) return SOBER_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -498,6 +654,7 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
         case SOBER_MATERN32: ok = launch_family<SOBER_MATERN32>(pl, p, st); break;
         case SOBER_MATERN52: ok = launch_family<SOBER_MATERN52>(pl, p, st); break;
         case SOBER_TANIMOTO: ok = launch_family<SOBER_TANIMOTO>(pl, p, st); break;
+        case SOBER_TANIMOTO_BITS: ok = launch_bits(pl, p, st); break;
     }
     if (!ok) return SOBER_ERR_UNSUPPORTED;
     SOBER_LAUNCH_CHECK("group_accumulate");

@@ -78,6 +78,28 @@ __global__ void row_sqnorm_kernel(const double* __restrict__ X, int64_t ldx, int
     if (lane == 0) out[i] = s;
 }
 
+// ---- bit packing of {0,1} rows: one warp per row, ballot packs 32 entries per step ---------------------------
+__global__ void pack_bits_kernel(const double* __restrict__ X, int64_t ldx, int64_t n, int d, int W,
+                                 uint64_t* __restrict__ words, double* __restrict__ popc, int* __restrict__ not_binary) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const double* x = X + i * ldx;
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(words + i * W);
+    int count = 0;
+    bool bad = false;
+    for (int k0 = 0; k0 < W * 64; k0 += 32) {
+        const int k = k0 + lane;
+        const double v = k < d ? x[k] : 0.0;
+        bad |= (v != 0.0 && v != 1.0);
+        const unsigned m = __ballot_sync(0xffffffffu, v != 0.0);
+        if (lane == 0) out32[k0 >> 5] = m;       // little-endian: 32-bit half (k0 / 32) of word k0 / 64
+        count += __popc(m);
+    }
+    if (lane == 0) popc[i] = (double)count;
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(not_binary, 1);
+}
+
 // ---- non-zero compaction (stable) ---------------------------------------------------------------------
 constexpr int CP_THREADS = 256;
 constexpr int CP_ITEMS = 8;  // consecutive items per thread: keeps the output order
@@ -272,6 +294,17 @@ extern "C" int sober_make_records(const double* X, int64_t ldx, int32_t d, const
     make_records_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, d, center, inv_ls, idx, mu,
                                                                                       m, rec, ldr);
     SOBER_LAUNCH_CHECK("make_records");
+    return SOBER_OK;
+}
+
+extern "C" int sober_pack_bits(const double* X, int64_t ldx, int64_t n, int32_t d, uint64_t* words, int32_t ldw,
+                               double* popc, int32_t* not_binary, void* stream) {
+    if (n < 0 || d <= 0 || ldx < d || ldw < (d + 63) / 64 || (n > 0 && (!X || !words || !popc || !not_binary)))
+        return SOBER_ERR_ARG;
+    if (n == 0) return SOBER_OK;
+    pack_bits_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(X, ldx, n, d, ldw, words, popc,
+                                                                                       not_binary);
+    SOBER_LAUNCH_CHECK("pack_bits");
     return SOBER_OK;
 }
 

@@ -12,13 +12,13 @@ import torch
 from oracle import rchq as oracle
 from sober_b200._ops import LandmarkTable, PointSet  # plain containers, no CUDA needed
 
-RBF, MATERN12, MATERN32, MATERN52, TANIMOTO = range(5)
+RBF, MATERN12, MATERN32, MATERN52, TANIMOTO, TANIMOTO_BITS = range(6)
 
 
 def kernel_values(dot, xn, zn, family):
     """dot: (m, L) = x . zt ; xn: (m, 1) ; zn: (1, L).  Same convention as csrc/common.cuh: the family constant
     is already folded into the coordinates (sober_b200._lib.FAMILY_SCALE)."""
-    if family == TANIMOTO:
+    if family in (TANIMOTO, TANIMOTO_BITS):
         return ((dot + 1e-6) / (1e-6 + xn + zn - dot)).clamp_min(0)
     d2 = (xn + zn + dot).clamp_min(0)
     if family == RBF:
@@ -61,6 +61,11 @@ class TorchOps:
     def raw_points(self, X):
         n, d = X.shape
         return PointSet(X, X.stride(0), (X * X).sum(-1), 1, n, d)
+
+    def pack_bits(self, X):
+        """Test double: the 'words' are the float rows themselves (the popcount path is exercised on the GPU)."""
+        ok = bool(((X == 0) | (X == 1)).all())
+        return X, (X != 0).sum(-1).to(torch.float64), ok
 
     def compact_nonzero(self, mu):
         idx = torch.nonzero(mu != 0).reshape(-1).to(torch.int32)

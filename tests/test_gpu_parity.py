@@ -54,12 +54,13 @@ def spec_tables(rec, case, dev):
 def test_gram_matches_oracle(ops, cuda_device, name, variant):
     from sober_b200 import Recombiner, configure
     case = Case(name, cuda_device)
-    if variant == 0 and case.X.shape[1] > 8:
+    if variant == 0 and case.X.shape[1] > 8 and case.fam != "tanimoto":
         pytest.skip("register kernel covers d <= 8")
     with configure(k1_variant=variant) as opts:
         rec = Recombiner(ops, opts=opts)
         ops.variant = variant
         kern, spec, center, inv_ls = spec_tables(rec, case, cuda_device)
+        rec._bits = variant == 0 and case.fam == "tanimoto"          # bit-packed popcount kernel
         try:
             table = rec._table(case.Z, spec, center, inv_ls)
             got_zz = rec._gram_T(rec._points(case.Z, spec, center, inv_ls), table).T
@@ -106,7 +107,7 @@ def test_group_accumulate_matches_oracle_trace(ops, cuda_device, name, variant):
     case = Case(name)                                   # oracle on the CPU
     if case.objective is not None:
         pytest.skip("objective branch covered end-to-end")
-    if variant == 0 and case.X.shape[1] > 8:
+    if variant == 0 and case.X.shape[1] > 8 and case.fam != "tanimoto":
         pytest.skip("register kernel covers d <= 8")
     groups, updates = [], []
 
@@ -131,6 +132,7 @@ def test_group_accumulate_matches_oracle_trace(ops, cuda_device, name, variant):
         with configure(k1_variant=variant) as opts:
             rec = Recombiner(ops, opts=opts, basis=dcase.U)
             kern, spec, center, inv_ls = spec_tables(rec, dcase, cuda_device)
+            rec._bits = variant == 0 and case.fam == "tanimoto"
             U, Uext, table = rec._nystrom(dcase.Z, case.b - 1, kern, spec, center, inv_ls)
             records = rec._use_records(spec, dcase.X.shape[1])
             st = {"spec": spec, "table": table, "pts": None if records else rec._points(dcase.X, spec, center, inv_ls)}
@@ -312,6 +314,41 @@ def test_make_records(ops, cuda_device, n, d):
     assert bool((ps.rec[:, d + 2:] == 0).all())
     full = ops.make_records(X, c, s)
     assert full.rec.shape[0] == n and bool((full.rec[:, d + 1] == 1).all())
+
+
+@pytest.mark.parametrize("n,d", [(1000, 24), (513, 64), (777, 100), (2000, 256), (300, 1024), (100, 2048), (50, 1500)])
+def test_pack_bits(ops, cuda_device, n, d):
+    import numpy as np
+    g = torch.Generator().manual_seed(d)
+    X = (torch.rand(n, d, generator=g) < 0.1).to(torch.float64)
+    words, popc, ok = ops.pack_bits(X.to(cuda_device))
+    assert ok and words.shape[0] == n and words.shape[1] * 64 >= d
+    bits = np.unpackbits(words.cpu().numpy().view(np.uint8), axis=1, bitorder="little")
+    assert np.array_equal(bits[:, :d], X.numpy().astype(np.uint8))
+    assert not bits[:, d:].any()
+    assert torch.equal(popc.cpu(), X.sum(-1))
+    X[n // 2, d // 3] = 0.5
+    assert not ops.pack_bits(X.to(cuda_device))[2]
+
+
+@pytest.mark.parametrize("d,density", [(1024, 0.05), (2048, 0.02), (512, 0.3), (167, 0.2)])
+def test_tanimoto_popcount_gram_matches_oracle(ops, cuda_device, d, density):
+    """Bit-packed Tanimoto (popcount) against the oracle's float Tanimoto: exact integer dot products, so the only
+    difference is the rounding of the division."""
+    from sober_b200 import Recombiner
+    from sober_b200._kernel_spec import introspect
+    g = torch.Generator().manual_seed(d)
+    X = (torch.rand(3000, d, generator=g) < density).to(torch.float64).to(cuda_device)
+    X[5] = 0                                                     # an all-zero fingerprint: eps keeps it finite
+    Z = X[torch.randperm(3000, generator=g)[:333].to(cuda_device)].clone()
+    kern = ok.Kernel(ok.BareModel(ok.make_kernel("tanimoto", 1.0, 1.9).to(cuda_device)), mode="kernel")
+    rec = Recombiner(ops)
+    rec._bits = True
+    spec = introspect(kern)
+    center, inv_ls = scaled(spec, Z, cuda_device)
+    got = rec._gram_T(rec._points(X, spec, center, inv_ls), rec._table(Z, spec, center, inv_ls)).T
+    want = kern(Z, X)
+    assert rel(got, want) < 1e-13
 
 
 def test_scatter_result(ops, cuda_device):
