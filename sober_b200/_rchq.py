@@ -269,7 +269,10 @@ class Recombiner:
         UextT = Uext.T.contiguous()
 
         idx, mass, n_local = ops.compact_nonzero(mu)
-        alive = Alive(idx, mass, ops.make_records(X, center, inv_ls, idx, mass).rec if records else None)
+        # every weight non-zero (the usual case): the alive-list is the identity and the record pass reads X as one
+        # contiguous stream instead of gathering rows
+        gather = None if n_local == n_rows else idx
+        alive = Alive(idx, mass, ops.make_records(X, center, inv_ls, gather, mass).rec if records else None)
         live = comm.all_gather_ints(n_local, dev)
         pos0, remaining = sum(live[:comm.rank]), sum(live)
         obj = None if calc_obj is None else (-1 * calc_obj(pts_rec.to(dev))).to(torch.float64)
