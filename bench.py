@@ -227,6 +227,8 @@ def main():
         barrier()
     elapsed_ms = t_start.elapsed_time(t_end)
     timing = ops.timing_summary()
+    uc_big = ops.timing_largest("update_compact")
+    k1_big = ops.timing_largest("group_accumulate")
     ops.timing = None
     launches = ops.launches - launches0
     if world > 1:
@@ -296,7 +298,10 @@ def main():
     k1_calls, k1_ms, k1_pairs = timing.get("group_accumulate", (0, 0.0, 0))
     k1_tflops = k1_pairs * flop_per_pair / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else None
     uc_calls, uc_ms, uc_bytes = timing.get("update_compact", (0, 0.0, 0))
-    uc_gbs = uc_bytes / (uc_ms * 1e-3) / 1e9 if uc_ms > 0 else None
+    # HBM roofline of the streaming pass: the pass over ALL candidates (first iteration); later iterations halve
+    uc_gbs = uc_big[1] / (uc_big[0] * 1e-3) / 1e9 if uc_big and uc_big[0] > 0 else None
+    bits = fam == "tanimoto" and d > 8
+    words = (d + 63) // 64
     car_calls, car_ms, car_steps = timing.get("car_eliminate", (0, 0.0, 0))
     step_ms = elapsed_ms / args.steps
 
@@ -312,8 +317,8 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
-        "roofline": {
-            "kernel": "group_accumulate (K1: fused cross-kernel + weighted group sums)",
+        "roofline": ({
+            "kernel": "group_accumulate (K1: fused cross-kernel + weighted group sums, record layout)",
             "bound": "fp64",          # FP64 FMA pipe; the hbm|tensor enum has no entry for it
             "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": (k1_tflops / fp64_peak) if k1_tflops else None,
@@ -322,16 +327,29 @@ def main():
             "algorithmic_flop_per_pair": flop_per_pair, "pairs_per_step": k1_pairs / max(args.steps, 1),
             "launches": k1_calls, "ms_per_step": k1_ms / max(args.steps, 1),
             "share_of_step": k1_ms / elapsed_ms if elapsed_ms else None,
-        },
+            "largest_launch": {"ms": k1_big[0], "pairs": k1_big[1],
+                               "tflops": k1_big[1] * flop_per_pair / (k1_big[0] * 1e-3) / 1e12} if k1_big else None,
+        } if not bits else {
+            "kernel": "group_accumulate (K1, bit-packed Tanimoto: popcount(x & z) + FP64 ratio)",
+            "bound": "int",           # integer pipe (AND + POPC); no measured peak for it on this pool
+            "achieved": k1_pairs * words / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None, "peak": None,
+            "unit": "G word-op/s (64-bit AND+POPC)", "frac": None, "traffic": None,
+            "algorithmic_word_ops_per_pair": words, "pairs_per_step": k1_pairs / max(args.steps, 1),
+            "launches": k1_calls, "ms_per_step": k1_ms / max(args.steps, 1),
+            "share_of_step": k1_ms / elapsed_ms if elapsed_ms else None,
+        }),
         "roofline_stream": {
-            "kernel": "update_compact (weight update + alive-list compaction)", "bound": "hbm",
-            "achieved": uc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (uc_gbs / hbm_peak) if uc_gbs else None,
-            "peak_source": hbm_src, "bytes_per_step": uc_bytes / max(args.steps, 1),
-            "ms_per_step": uc_ms / max(args.steps, 1),
+            "kernel": "update_compact (weight update + alive-list compaction, moves the record rows): "
+                      "the launch over all candidates",
+            "bound": "hbm", "achieved": uc_gbs, "peak": hbm_peak, "unit": "GB/s",
+            "frac": (uc_gbs / hbm_peak) if uc_gbs else None, "peak_source": hbm_src,
+            "bytes": uc_big[1] if uc_big else None, "ms": uc_big[0] if uc_big else None,
+            "all_launches_ms_per_step": uc_ms / max(args.steps, 1),
         },
         "stage_ms_per_step": {k: v[1] / max(args.steps, 1) for k, v in timing.items()},
-        "car": {"calls_per_step": car_calls / max(args.steps, 1),
-                "us_per_elimination_step": 1e3 * car_ms / car_steps if car_steps else None},
+        "car": {name_: {"calls_per_step": timing[name_][0] / max(args.steps, 1),
+                        "us_per_sequential_step": 1e3 * timing[name_][1] / timing[name_][2] if timing[name_][2] else None}
+                for name_ in ("car_cluster", "car_eliminate") if name_ in timing},
     }
     if world == 1 and not args.no_cpu_baseline:
         sample = min(args.cpu_sample, n_rec)

@@ -82,6 +82,14 @@ class CudaOps:
         ev.record(torch.cuda.current_stream(self.device))
         self.timing.setdefault(name, []).append((start, ev, work))
 
+    def timing_largest(self, name):
+        """(ms, work) of the launch with the most work recorded under ``name`` -- call after a synchronize."""
+        recs = (self.timing or {}).get(name, [])
+        if not recs:
+            return None
+        a, b, w = max(recs, key=lambda r: r[2])
+        return a.elapsed_time(b), w
+
     def timing_summary(self):
         """{name: (calls, total_ms, total_work)} -- call after a synchronize."""
         out = {}
