@@ -17,7 +17,27 @@ def nullspace_rows(design, how):
     if how == "qr":
         q = torch.linalg.qr(design, mode="complete").Q
         return q[:, dim:].T.contiguous()
+    if how == "projector":
+        return projector_rows(design)
     raise ValueError(how)
+
+
+def projector_rows(design, thin_q=None):
+    """Null-space basis from the orthogonal projector: the trailing k columns of P = I - Q1 Q1^T, Q1 an orthonormal
+    basis of range(design).  Spans null(design^T) whenever the leading n' x n' block of Q1 is non-singular (generic);
+    NOT orthonormal -- the elimination only needs a basis, its ratio tests are invariant to column scaling.
+
+    Everything is GEMM-shaped (no n'-step Householder sequence): columns of the design are normalised (does not
+    change the null space), Q1 comes from Cholesky-QR applied twice (the projector does not see column signs, so a
+    Householder Q1 gives the same matrix -- that is what the oracle-side check uses), then one GEMM."""
+    from ._nystrom import _orthonormal_basis
+    pts, dim = design.shape
+    if thin_q is None:
+        scaled = design / design.norm(dim=0, keepdim=True).clamp_min(1e-300)
+        thin_q = _orthonormal_basis(scaled, "cholqr2", check=False)     # no host sync; see caratheodory()
+    rows = -(thin_q[dim:, :] @ thin_q.mH)                       # (k x S): - Q1[n':, :] Q1^T
+    rows[:, dim:] += torch.eye(pts - dim, dtype=design.dtype, device=design.device)
+    return rows.contiguous()
 
 
 def caratheodory(ops, feats, mass, how, nullspace=None):
@@ -38,9 +58,16 @@ def caratheodory(ops, feats, mass, how, nullspace=None):
         ops.car_cluster(out, design=design)
         return out
     rows = nullspace(design) if nullspace is not None else nullspace_rows(design, how)
-    exact = nullspace is not None or how != "qr"          # parity / injected bases keep the reference's rounding
+    exact = nullspace is not None or how == "svd"          # parity / injected bases keep the reference's rounding
     if fits is not None and fits(pts, dim, True):
         ops.car_cluster(out, basis_rows=rows, exact=exact)
     else:
         ops.car_eliminate(rows, out, exact=exact)
     return out
+
+
+def needs_retry(how, kept_count, dim, finite):
+    """The projector basis can be rank-deficient (singular leading block of Q1) or its Cholesky-QR can break down;
+    both show up as more than n' survivors or non-finite weights.  The caller checks this with the sync it does
+    anyway and redoes the step with the Householder basis."""
+    return how == "projector" and (kept_count > dim or not finite)

@@ -17,11 +17,11 @@ def draw_test_matrix(rows, cols, dtype, device):
     return torch.randn(rows, cols, dtype=dtype, device=device)
 
 
-def _orthonormal_basis(y, how):
+def _orthonormal_basis(y, how, check=True):
     """Q of the thin QR of y (m x q, m >= q).
 
     ``householder``: torch.linalg.qr (cuSOLVER geqrf + orgqr: ~1.2 ms for 1000 x 199 on B200, an unblocked panel
-    kernel).  ``cholqr2``: Cholesky-QR applied twice -- two Gram GEMMs, two q x q Cholesky factorisations, two
+    kernel).  ``check=False`` skips the (synchronising) breakdown test.  ``cholqr2``: Cholesky-QR applied twice -- two Gram GEMMs, two q x q Cholesky factorisations, two
     triangular solves; mathematically the same Q up to column signs (the QR factorisation of a full-rank matrix is
     unique up to signs, and the final basis U = Q svd(Q^T K).U does not see them), numerically orthonormal to
     rounding while cond(y) < ~1e8.  Falls back to Householder when a Cholesky factorisation breaks down
@@ -31,7 +31,8 @@ def _orthonormal_basis(y, how):
         for _ in range(2):
             gram = q.mH @ q
             chol, info = torch.linalg.cholesky_ex(gram)
-            if int(info) != 0:
+            # check=False: no host sync; a breakdown leaves NaNs that the caller detects downstream
+            if check and int(info) != 0:
                 return torch.linalg.qr(y).Q
             q = torch.linalg.solve_triangular(chol.mH, q, upper=True, left=False)
         return q

@@ -322,12 +322,19 @@ class Recombiner:
             bary = bary / totw.unsqueeze(1)
             clock.lap("tail+project")
             wfull = _car.caratheodory(ops, bary, totw, o.nullspace, self.nullspace)
+            kept = wfull > 0
+            flags = torch.cat([kept, torch.isfinite(wfull).all().reshape(1)]).tolist()   # the one host sync of the iteration
+            if self.nullspace is None and _car.needs_retry(o.nullspace, sum(flags[:-1]), bary.shape[1] + 1, flags[-1]):
+                wfull = _car.caratheodory(ops, bary, totw, "qr")
+                kept = wfull > 0
+                flags = kept.tolist() + [True]
             clock.lap("car")
             if obj is not None:
                 wfull = self._objective_step(bary[:, :n], bary[:, n], wfull)
-            kept = wfull > 0
+                kept = wfull > 0
+                flags = kept.tolist() + [True]
             rank = (torch.cumsum(kept.to(torch.int32), 0) - kept.to(torch.int32)).to(torch.int32)
-            keep = KeepMap(kept.tolist(), S, ES)              # the one host sync of the iteration
+            keep = KeepMap(flags[:-1], S, ES)
             new_pos0 = keep.before(pos0)
             new_local = keep.before(pos0 + n_local) - new_pos0
             alive = Alive(*ops.update_compact(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, keep.K,
@@ -377,6 +384,9 @@ class Recombiner:
             alive_obj = obj[all_idx]
             feats = torch.cat([feats, alive_obj.unsqueeze(1)], 1)
         wfull = _car.caratheodory(ops, feats, all_mass, o.nullspace, self.nullspace)
+        if self.nullspace is None and o.nullspace == "projector":
+            if _car.needs_retry("projector", int((wfull > 0).sum()), feats.shape[1] + 1, bool(torch.isfinite(wfull).all())):
+                wfull = _car.caratheodory(ops, feats, all_mass, "qr")
         if obj is not None:
             # NB the reference indexes ``obj`` with POSITIONS here (SOBER/_rchq.py:89), kept as is
             live = torch.nonzero(wfull > 0).reshape(-1)

@@ -12,8 +12,10 @@ L x L / S x S steps imitate the reference:
                    run on the same device.
 ``mode="fast"``    Gram from the CUDA kernel (symmetric), the gate reduced to what it does in practice for an
                    (always bitwise-asymmetric) gpytorch Gram -- ``sqrt(K*K^T)`` then Cholesky with escalating
-                   jitter -- and a Householder-QR null space.  Same algorithm, different (equally valid) null-space
-                   basis: weights/moments invariants hold, indices are those of the oracle run with the same basis.
+                   jitter -- and the null space taken as the trailing columns of the orthogonal projector
+                   I - Q1 Q1^T (``nullspace="projector"``; ``"qr"`` = trailing columns of the complete Householder Q is
+                   also available).  Same algorithm, different (equally valid) null-space basis: weights/moments
+                   invariants hold, indices are those of the oracle run with the same basis.
 
 Every knob can be set individually; ``SOBER_B200_MODE`` picks the preset at import.
 """
@@ -22,7 +24,7 @@ import os
 
 _PRESETS = {
     "parity": dict(gram="callable", gate="reference", nullspace="svd", nystrom_qr="householder"),
-    "fast": dict(gram="cuda", gate="cholesky", nullspace="qr", nystrom_qr="cholqr2"),
+    "fast": dict(gram="cuda", gate="cholesky", nullspace="projector", nystrom_qr="cholqr2"),
 }
 
 

@@ -46,3 +46,14 @@ class Case:
         if self.mode == "kernel":
             return ok.Kernel(ok.BareModel(cov), mode="kernel")
         return ok.Kernel(ok.GPModel(cov, self.Xobs, None, noise=self.noise), mode=self.mode)
+
+
+def projector_nullspace(design):
+    """Oracle-side restatement of the fast mode's null-space basis (sober_b200/_car.py::projector_rows): trailing
+    columns of I - Q1 Q1^T with Q1 from LAPACK's Householder QR (the projector does not depend on how Q1 was
+    orthonormalised).  Returns Phi (S x k) for oracle.recombination(nullspace=...)."""
+    pts, dim = design.shape
+    q1 = torch.linalg.qr(design / design.norm(dim=0, keepdim=True)).Q
+    phi = -(q1 @ q1[dim:, :].T)
+    phi[dim:, :] += torch.eye(pts - dim, dtype=design.dtype)
+    return phi

@@ -12,7 +12,7 @@ import torch
 
 from oracle import kernels as ok
 from oracle import rchq as oracle
-from _cases import CASES, LOOP_CASES, Case
+from _cases import CASES, LOOP_CASES, Case, projector_nullspace
 
 pytestmark = pytest.mark.gpu
 STABLE = [c for c in CASES if c != "rbf2d_branin"]
@@ -417,16 +417,14 @@ def test_parity_mode_equals_oracle_on_same_device(ops, cuda_device, name):
 
 
 @pytest.mark.parametrize("name", ["matern6d_rest", "matern6d_pow2", "rbf_ard5d", "tanimoto256", "predcov_matern6d"])
-def test_fast_mode_equals_cpu_oracle_with_qr_nullspace(ops, cuda_device, name):
-    """fast mode (CUDA Gram, Cholesky gate, Householder-QR null space on cuSOLVER) vs the CPU oracle fed the same
-    test matrix and a LAPACK QR null space."""
+def test_fast_mode_equals_cpu_oracle_with_projector_nullspace(ops, cuda_device, name):
+    """fast mode (CUDA Gram, Cholesky gate, projector null space, cluster elimination kernel) vs the CPU oracle fed
+    the same test matrix and the same null-space construction restated with LAPACK (tests/_cases.py)."""
     import sober_b200
     from sober_b200 import _nystrom
     cpu = Case(name)
     R = torch.randn(cpu.Z.shape[0], cpu.b - 1, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
 
-    def qr_null(design):
-        return torch.linalg.qr(design, mode="complete").Q[:, design.shape[1]:]
     orig = torch.randn
     torch.randn = lambda *a, **k: R.clone() if tuple(a[:2]) == tuple(R.shape) else orig(*a, **k)
     try:
@@ -434,7 +432,7 @@ def test_fast_mode_equals_cpu_oracle_with_qr_nullspace(ops, cuda_device, name):
             warnings.simplefilter("ignore")
             mu_o = None if cpu.mu is None else cpu.mu.clone()
             idx_o, w_o = oracle.recombination(cpu.X, cpu.Z, cpu.b, cpu.kernel(), None, None, init_weights=mu_o,
-                                              nullspace=qr_null)
+                                              nullspace=projector_nullspace)
     finally:
         torch.randn = orig
     gpu = Case(name, cuda_device)

@@ -10,7 +10,7 @@ from oracle import rchq as oracle
 from sober_b200 import Recombiner, configure
 from sober_b200._rchq import KeepMap
 from sober_b200 import _nystrom
-from _cases import LOOP_CASES, CASES, Case
+from _cases import LOOP_CASES, CASES, Case, projector_nullspace
 from _cpu_ops import TorchOps
 
 # rbf2d_branin is the chaotic regime (rank-deficient Gram, SURVEY.md TL;DR 6): a 1e-16 change in the group sums
@@ -63,14 +63,12 @@ def test_generic_callable_path_matches_fused(name):
 
 
 @pytest.mark.parametrize("name", ["matern6d_rest", "matern6d_pow2", "rbf_ard5d", "tanimoto256"])
-def test_fast_mode_equals_oracle_with_qr_nullspace(name):
-    """fast mode = the reference algorithm with a Householder-QR null-space basis: feed that basis through the
+def test_fast_mode_equals_oracle_with_projector_nullspace(name):
+    """fast mode = the reference algorithm with a projector null-space basis (trailing columns of I - Q1 Q1^T): feed that basis through the
     ORACLE's elimination and the same points come out."""
     case = Case(name)
     R = torch.randn(case.Z.shape[0], case.b - 1, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
 
-    def qr_null(design):
-        return torch.linalg.qr(design, mode="complete").Q[:, design.shape[1]:]
     orig = torch.randn
     torch.randn = lambda *a, **k: R.clone() if tuple(a[:2]) == tuple(R.shape) else orig(*a, **k)
     try:
@@ -78,7 +76,7 @@ def test_fast_mode_equals_oracle_with_qr_nullspace(name):
             warnings.simplefilter("ignore")
             mu_o = None if case.mu is None else case.mu.clone()
             idx_o, w_o = oracle.recombination(case.X, case.Z, case.b, case.kernel(), None, None, init_weights=mu_o,
-                                              nullspace=qr_null)
+                                              nullspace=projector_nullspace)
     finally:
         torch.randn = orig
     _nystrom._injected_test_matrix = R
