@@ -349,7 +349,7 @@ def main():
         "stage_ms_per_step": {k: v[1] / max(args.steps, 1) for k, v in timing.items()},
         "car": {name_: {"calls_per_step": timing[name_][0] / max(args.steps, 1),
                         "us_per_sequential_step": 1e3 * timing[name_][1] / timing[name_][2] if timing[name_][2] else None}
-                for name_ in ("car_cluster", "car_eliminate") if name_ in timing},
+                for name_ in ("car_cols", "car_cluster", "car_eliminate") if name_ in timing},
     }
     if world == 1 and not args.no_cpu_baseline:
         sample = min(args.cpu_sample, n_rec)

@@ -177,6 +177,16 @@ int sober_car_cluster(const double* design, const double* basis, int32_t S, int3
 int sober_car_cluster_profiled(const double* design, const double* basis, int32_t S, int32_t np, double* mu,
                                int32_t exact, int32_t* info, int64_t* prof, void* stream);
 
+/* Elimination only (SOBER/_rchq.py:237-266) on a given basis (k x S rows, DESTROYED is not -- it is only read),
+ * column-distributed over an 8-CTA cluster with the matrix in registers: no cross-CTA reduction per step, one
+ * broadcast of the pivot column.  Covers k <= 256, S <= 448; sober_car_cluster_cols_fits returns 0 otherwise.
+ * exact as in sober_car_cluster.  mu (S) updated in place; info[0] (may be NULL) = steps taken. */
+int sober_car_cluster_cols_fits(int32_t S, int32_t k);
+int sober_car_cluster_cols(double* basis, int32_t k, int32_t S, double* mu, int32_t exact, int32_t* info, void* stream);
+/* Same with 8 int64 cycle counters (CTA 0 / thread 0) written to prof (diagnostics). */
+int sober_car_cluster_cols_profiled(double* basis, int32_t k, int32_t S, double* mu, int32_t exact, int32_t* info,
+                                    int64_t* prof, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Weight update + compaction of the alive-list (SOBER/_rchq.py:198-221).
  *   For local position j (global p = pos0 + j):

@@ -59,7 +59,10 @@ def caratheodory(ops, feats, mass, how, nullspace=None):
         return out
     rows = nullspace(design) if nullspace is not None else nullspace_rows(design, how)
     exact = nullspace is not None or how == "svd"          # parity / injected bases keep the reference's rounding
-    if fits is not None and fits(pts, dim, True):
+    cols_fit = getattr(ops, "car_cols_fits", None)
+    if cols_fit is not None and cols_fit(pts, rows.shape[0]):
+        ops.car_cols(rows, out, exact=exact)                # column-distributed cluster kernel (fastest)
+    elif fits is not None and fits(pts, dim, True):
         ops.car_cluster(out, basis_rows=rows, exact=exact)
     else:
         ops.car_eliminate(rows, out, exact=exact)

@@ -58,6 +58,9 @@ PROTOTYPES = {
     "sober_car_cluster_fits": (C.c_int, [_I32, _I32, _I32]),
     "sober_car_cluster": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P, _P]),
     "sober_car_cluster_profiled": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, _P, _P, _P]),
+    "sober_car_cluster_cols_fits": (C.c_int, [_I32, _I32]),
+    "sober_car_cluster_cols": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P]),
+    "sober_car_cluster_cols_profiled": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P]),
     "sober_update_compact": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _I32, _I32, _I64, _P, _P,
                                        _P, _P, _I64, _I32, _P]),
     "sober_scatter_result": (C.c_int, [_P, _I64, _P, _P, _I64, _P]),

@@ -252,6 +252,21 @@ class CudaOps:
             self._end("car_cluster", t0, (S - n_prime) + (0 if basis_rows is not None else 2 * n_prime))
         self.launches += 1
 
+    def car_cols_fits(self, S, k):
+        with torch.cuda.device(self.device):
+            return int(self.lib.sober_car_cluster_cols_fits(int(S), int(k)))
+
+    def car_cols(self, basis_rows, mass, exact=False):
+        """Elimination on ``basis_rows`` (k x S) with the column-distributed cluster kernel; ``mass`` reduced in place."""
+        k, S = basis_rows.shape
+        assert basis_rows.is_contiguous() and mass.is_contiguous()
+        with torch.cuda.device(self.device):
+            t0 = self._begin("car_cols")
+            check(self.lib.sober_car_cluster_cols(_ptr(basis_rows), k, S, _ptr(mass), int(bool(exact)), None,
+                                                  self._stream()), "car_cluster_cols")
+            self._end("car_cols", t0, k)
+        self.launches += 1
+
     # -- update + compaction ----------------------------------------------------------------------------------
     def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out,
                        rec=None, d=0):

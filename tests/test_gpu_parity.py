@@ -198,6 +198,43 @@ def test_car_cluster_elimination_bitwise(ops, cuda_device, name):
         assert torch.equal(mass[keep], case.car(i, "w"))
 
 
+@pytest.mark.parametrize("name", STABLE + ["rbf2d_branin"])
+def test_car_cols_elimination_bitwise(ops, cuda_device, name):
+    """The column-distributed cluster kernel in EXACT mode on the reference's own null-space bases: bit-identical."""
+    case = Case(name, cuda_device)
+    if case.n_car == 0:
+        pytest.skip("no CAR call in this fixture")
+    for i in range(case.n_car):
+        phi = case.car(i, "Phi")
+        assert ops.car_cols_fits(phi.shape[0], phi.shape[1]) > 0
+        mass = case.car(i, "mu").clone().contiguous()
+        ops.car_cols(phi.T.contiguous(), mass, exact=True)
+        torch.cuda.synchronize()
+        keep = mass > 0
+        assert torch.equal(torch.nonzero(keep).reshape(-1), case.car(i, "idx"))
+        assert torch.equal(mass[keep], case.car(i, "w"))
+
+
+@pytest.mark.parametrize("S,n_prime", [(400, 200), (448, 200), (200, 100), (96, 41), (33, 7), (401, 199)])
+def test_car_cols_projector_basis(ops, cuda_device, S, n_prime):
+    """Fast mode at bench size: projector null space + column-distributed elimination vs the same basis through the
+    oracle's elimination (support identical, weights 1e-10, moments preserved)."""
+    from sober_b200 import _car
+    g = torch.Generator().manual_seed(S + n_prime)
+    feats = torch.randn(S, n_prime - 1, dtype=torch.float64, generator=g) * \
+        torch.logspace(0, -4, n_prime - 1, dtype=torch.float64)
+    mass = torch.rand(S, dtype=torch.float64, generator=g)
+    mass /= mass.sum()
+    design = torch.cat([torch.ones(S, 1, dtype=torch.float64), feats], 1)
+    got = _car.caratheodory(ops, feats.to(cuda_device), mass.to(cuda_device), "projector").cpu()
+    want = mass.clone()
+    oracle.eliminate(projector_nullspace(design), want, oracle.Factory())
+    assert int((got > 0).sum()) <= n_prime
+    assert torch.equal(got > 0, want > 0)
+    assert float((got - want).abs().max()) < 1e-10
+    assert float((design.T @ got - design.T @ mass).abs().max()) < 1e-12
+
+
 @pytest.mark.parametrize("S,n_prime", [(48, 24), (400, 200), (96, 41), (200, 100), (33, 7)])
 def test_car_cluster_fused_qr(ops, cuda_device, S, n_prime):
     """QR + null space + elimination in one kernel vs LAPACK QR + the oracle's elimination: same support, same
