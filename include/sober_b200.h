@@ -206,6 +206,15 @@ int sober_update_compact(const int32_t* idx_in, const double* mu_in, int64_t n_l
 int sober_scatter_result(double* dst, int64_t n, const int64_t* idx, const double* w, int64_t m, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Small dense helper of the Cholesky-QR steps (Nystrom range finder, projector null space):
+ *   solve X * R = Y for upper-triangular R (q x q row-major, q <= 256), Y and X m x q row-major (X may alias Y).
+ * One warp per row, the row in registers.  Replaces torch.linalg.solve_triangular (cuBLAS trsm: ~0.1 ms per call at
+ * q = 200, called ~40 times per recombination).
+ * ------------------------------------------------------------------------------------------------- */
+int sober_trsm_right_upper(const double* Y, int64_t ldy, const double* R, int64_t ldr, int32_t m, int32_t q, double* X,
+                           int64_t ldx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Diagnostics: FP64 FMA throughput probe (the roofline denominator for K1, which is FP64-pipe bound).
  * Launches `blocks` x 256 threads, each doing iters * 8 dependent-chain DFMAs; flops = blocks*256*iters*16.
  * ------------------------------------------------------------------------------------------------- */

@@ -22,22 +22,37 @@ def nullspace_rows(design, how):
     raise ValueError(how)
 
 
-def projector_rows(design, thin_q=None):
+def projector_rows(design, thin_q=None, with_defect=False):
     """Null-space basis from the orthogonal projector: the trailing k columns of P = I - Q1 Q1^T, Q1 an orthonormal
     basis of range(design).  Spans null(design^T) whenever the leading n' x n' block of Q1 is non-singular (generic);
     NOT orthonormal -- the elimination only needs a basis, its ratio tests are invariant to column scaling.
 
-    Everything is GEMM-shaped (no n'-step Householder sequence): columns of the design are normalised (does not
-    change the null space), Q1 comes from Cholesky-QR applied twice (the projector does not see column signs, so a
-    Householder Q1 gives the same matrix -- that is what the oracle-side check uses), then one GEMM."""
-    from ._nystrom import _orthonormal_basis
+    Everything is GEMM-shaped (no n'-step Householder sequence).  Columns of the design are normalised (does not
+    change the null space); ONE Cholesky-QR pass gives Qt with Qt^T Qt = I + Delta, |Delta| ~ eps cond^2; the exact
+    projector I - Qt (I + Delta)^-1 Qt^T is then formed with the Neumann series (I + Delta)^-1 = I - Delta + Delta^2
+    (error |Delta|^3) -- three small GEMMs instead of a second Cholesky + triangular solve.  ``with_defect`` also
+    returns |Delta|_F (a device scalar) so that the caller can fall back when it is not small.  The projector does not
+    see how Q1 was orthonormalised: a Householder Q1 gives the same matrix (what the oracle-side check uses)."""
+    from ._linalg import solve_right_upper
     pts, dim = design.shape
-    if thin_q is None:
-        scaled = design / design.norm(dim=0, keepdim=True).clamp_min(1e-300)
-        thin_q = _orthonormal_basis(scaled, "cholqr2", check=False)     # no host sync; see caratheodory()
-    rows = -(thin_q[dim:, :] @ thin_q.mH)                       # (k x S): - Q1[n':, :] Q1^T
-    rows[:, dim:] += torch.eye(pts - dim, dtype=design.dtype, device=design.device)
-    return rows.contiguous()
+    eye_k = torch.eye(pts - dim, dtype=design.dtype, device=design.device)
+    if thin_q is not None:
+        rows = -(thin_q[dim:, :] @ thin_q.mH)
+        rows[:, dim:] += eye_k
+        return rows.contiguous()
+    scaled = design / design.norm(dim=0, keepdim=True).clamp_min(1e-300)
+    chol, _ = torch.linalg.cholesky_ex(scaled.mH @ scaled)          # no host sync: NaNs surface in the caller's check
+    qt = solve_right_upper(chol.mH, scaled)
+    delta = qt.mH @ qt
+    delta.diagonal().sub_(1.0)
+    inv = delta @ delta - delta
+    inv.diagonal().add_(1.0)                                         # I - Delta + Delta^2
+    rows = -((qt[dim:, :] @ inv) @ qt.mH)                            # (k x S)
+    rows[:, dim:] += eye_k
+    rows = rows.contiguous()
+    if with_defect:
+        return rows, torch.linalg.matrix_norm(delta)
+    return rows
 
 
 def caratheodory(ops, feats, mass, how, nullspace=None):
@@ -57,7 +72,13 @@ def caratheodory(ops, feats, mass, how, nullspace=None):
     if nullspace is None and how == "qr" and fits is not None and fits(pts, dim, False):
         ops.car_cluster(out, design=design)
         return out
-    rows = nullspace(design) if nullspace is not None else nullspace_rows(design, how)
+    defect = None
+    if nullspace is not None:
+        rows = nullspace(design)
+    elif how == "projector":
+        rows, defect = projector_rows(design, with_defect=True)
+    else:
+        rows = nullspace_rows(design, how)
     exact = nullspace is not None or how == "svd"          # parity / injected bases keep the reference's rounding
     cols_fit = getattr(ops, "car_cols_fits", None)
     if cols_fit is not None and cols_fit(pts, rows.shape[0]):
@@ -66,11 +87,15 @@ def caratheodory(ops, feats, mass, how, nullspace=None):
         ops.car_cluster(out, basis_rows=rows, exact=exact)
     else:
         ops.car_eliminate(rows, out, exact=exact)
+    if defect is not None:
+        # poison the result when the one-pass Cholesky-QR was not accurate enough for the Neumann correction
+        # (|Delta|^3 must stay below rounding): the caller's finite-check then redoes the step with Householder QR
+        out = torch.where(defect < 1e-5, out, torch.full_like(out, float("nan")))
     return out
 
 
 def needs_retry(how, kept_count, dim, finite):
-    """The projector basis can be rank-deficient (singular leading block of Q1) or its Cholesky-QR can break down;
-    both show up as more than n' survivors or non-finite weights.  The caller checks this with the sync it does
-    anyway and redoes the step with the Householder basis."""
+    """The projector basis can be rank-deficient (singular leading block of Q1), its Cholesky-QR can break down or be
+    too inaccurate (see ``caratheodory``); all show up as more than n' survivors or non-finite weights.  The caller
+    checks this with the sync it does anyway and redoes the step with the Householder basis."""
     return how == "projector" and (kept_count > dim or not finite)

@@ -5,6 +5,8 @@ through the randomised range finder of ``torch.svd_lowrank`` (Halko et al. alg. 
 """
 import torch
 
+from ._linalg import solve_right_upper
+
 # Tests can set this to inject a test matrix drawn elsewhere (e.g. on the CPU generator the oracle used).
 _injected_test_matrix = None
 
@@ -34,7 +36,7 @@ def _orthonormal_basis(y, how, check=True):
             # check=False: no host sync; a breakdown leaves NaNs that the caller detects downstream
             if check and int(info) != 0:
                 return torch.linalg.qr(y).Q
-            q = torch.linalg.solve_triangular(chol.mH, q, upper=True, left=False)
+            q = solve_right_upper(chol.mH, q)
         return q
     return torch.linalg.qr(y).Q
 
@@ -95,7 +97,7 @@ def _left_singular_vectors(b, max_sweeps=12, tol=1e-13):
         status = torch.stack([info.to(torch.float64).reshape(()), size.to(torch.float64).reshape(())]).tolist()
         if status[0] != 0:
             break
-        u = torch.linalg.solve_triangular(chol.mH, u, upper=True, left=False)
+        u = solve_right_upper(chol.mH, u)
         # converged, or stagnated at the noise floor eps * cond(b) / relgap of the closest pair (clustered spectrum):
         # the Jacobi SVD has the same intrinsic sensitivity there
         stalled = sweep >= 2 and status[1] < 1e-5 and status[1] > 0.25 * prev

@@ -17,6 +17,7 @@ list, group = position mod S, exactly the reshape of SOBER/_rchq.py:118-123.  Wi
 enabled (``sober_b200.distributed``) candidates are row-sharded: each rank owns a contiguous range of positions
 and the only collective per iteration is one all-reduce of the (S x L') accumulator.
 """
+import itertools
 import time
 
 import torch
@@ -67,9 +68,8 @@ class KeepMap:
 
     def __init__(self, kept_mask, S, ES):
         self.S, self.ES, self.E = S, ES, ES // S
-        self.cum = [0] * (S + 1)                 # cum[g] = number of kept groups below g
-        for g in range(S):
-            self.cum[g + 1] = self.cum[g] + (1 if kept_mask[g] else 0)
+        # cum[g] = number of kept groups below g
+        self.cum = [0] + list(itertools.accumulate(1 if k else 0 for k in kept_mask[:S]))
         self.K = self.cum[S]
         self.tail_keep = bool(kept_mask[S - 1])
 
@@ -325,6 +325,8 @@ class Recombiner:
             kept = wfull > 0
             flags = torch.cat([kept, torch.isfinite(wfull).all().reshape(1)]).tolist()   # the one host sync of the iteration
             if self.nullspace is None and _car.needs_retry(o.nullspace, sum(flags[:-1]), bary.shape[1] + 1, flags[-1]):
+                if o.stats is not None:
+                    o.stats["car_retries"] = o.stats.get("car_retries", 0) + 1
                 wfull = _car.caratheodory(ops, bary, totw, "qr")
                 kept = wfull > 0
                 flags = kept.tolist() + [True]

@@ -388,6 +388,22 @@ def test_tanimoto_popcount_gram_matches_oracle(ops, cuda_device, d, density):
     assert rel(got, want) < 1e-13
 
 
+@pytest.mark.parametrize("m,q", [(400, 200), (1000, 199), (37, 33), (513, 256), (8, 1)])
+def test_trsm_right_upper(ops, cuda_device, m, q):
+    from sober_b200._linalg import solve_right_upper
+    g = torch.Generator().manual_seed(m + q)
+    a = torch.randn(q + 5, q, dtype=torch.float64, generator=g)
+    r = torch.linalg.cholesky(a.T @ a).T.contiguous().to(cuda_device)        # well-conditioned upper factor
+    y = torch.randn(m, q, dtype=torch.float64, generator=g).to(cuda_device)
+    got = solve_right_upper(r, y)
+    want = torch.linalg.solve_triangular(r, y, upper=True, left=False)
+    assert rel(got, want) < 1e-11
+    assert rel(got @ r, y) < 1e-12
+    # non-contiguous upper view of a lower factor, as the callers pass it
+    low = r.T.contiguous()
+    assert rel(solve_right_upper(low.mH, y), want) < 1e-11
+
+
 def test_scatter_result(ops, cuda_device):
     dst = torch.rand(1000, dtype=torch.float64, device=cuda_device)
     idx = torch.tensor([3, 17, 999], device=cuda_device)

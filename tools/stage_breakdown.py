@@ -14,8 +14,9 @@ for rep in range(3):
         warnings.simplefilter("ignore")
         torch.manual_seed(7)
         sober_b200.recombination(X, Z, b, kern, dev, torch.float64, init_weights=mu.clone())
+retries = stats.pop("car_retries", 0)
 tot = sum(stats.values())
-print(desc)
+print(desc, "| CAR retries with the Householder basis:", retries)
 for k, v in stats.items():
     print("%-18s %8.3f ms  %5.1f%%" % (k, v, 100 * v / tot))
 print("%-18s %8.3f ms" % ("total (synced)", tot))
