@@ -38,7 +38,11 @@ enum sober_family {
     SOBER_MATERN32 = 2, /* (1+sqrt3 r) exp(-sqrt3 r)                                                      */
     SOBER_MATERN52 = 3, /* (1+sqrt5 r+5/3 r^2) exp(-sqrt5 r)                                              */
     SOBER_TANIMOTO = 4, /* max(0,(<x,z>+1e-6)/(1e-6+|x|^2+|z|^2-<x,z>))                                   */
-    SOBER_TANIMOTO_BITS = 5 /* the same on bit-packed {0,1} rows: <x,z> = popcount(x & z)  (sober_pack_bits)  */
+    SOBER_TANIMOTO_BITS = 5, /* the same on bit-packed {0,1} rows: <x,z> = popcount(x & z)  (sober_pack_bits)  */
+    SOBER_HAMMING_LUT = 6    /* any stationary kernel with one lengthscale on bit-packed {0,1} rows: the squared
+                                distance is the Hamming distance h = popcount(x ^ z) times a constant, so
+                                k = lut[h], lut (d + 1 doubles) supplied by the caller (examples/ising.py:
+                                ScaleKernel(RBFKernel) on {0,1}^24)                                              */
 };
 
 int sober_abi_version(void);
@@ -103,8 +107,9 @@ int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_out, double*
  * Stationary families expect coordinates pre-multiplied by the family constant (1/sqrt2 RBF, 1 Matern-1/2,
  * sqrt3 Matern-3/2, sqrt5 Matern-5/2): fold it into inv_ls.
  * Zt (L x d): landmark table -- stationary: -2 (z - c) * inv_ls ; Tanimoto: z.   zn (L): |.|^2 of the same.
- * SOBER_TANIMOTO_BITS (indexed layout only): X and Zt point to uint64 word rows from sober_pack_bits (ldx = words per
- *   row, d = number of BITS, a multiple-of-64 padded row), xn / zn are the popcounts as doubles.
+ * SOBER_TANIMOTO_BITS / SOBER_HAMMING_LUT (indexed layout only): X and Zt point to uint64 word rows from
+ *   sober_pack_bits (ldx = words per row, d = number of BITS), xn / zn are the popcounts as doubles (unused by the
+ *   LUT family), lut as described at the enum.
  * At: S x L (transposed on purpose: coalesced stores and it is the left operand of the projection).
  * workspace holds the per-split partial sums (deterministic two-stage reduction, no atomics).
  * variant: 0 = automatic (records -> register kernel, else tiled), 1 = force the generic tiled kernel.
@@ -133,6 +138,7 @@ typedef struct sober_group_args {
     int32_t unit_weights; /* record layout only: ignore the weight stored in the records (plain Gram) */
     const double* rec;    /* record layout (sober_make_records), row j = local position j; NULL = indexed layout */
     int64_t ldr;
+    const double* lut;    /* SOBER_HAMMING_LUT: d + 1 kernel values indexed by the Hamming distance */
 } sober_group_args;
 
 int64_t sober_group_accumulate_workspace(const sober_group_args* args);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("SOBER_B200_LIB") or os.path.join(_HERE, "libsober_b20
 OK = 0
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "unsupported shape/family", 4: "workspace too small"}
 
-RBF, MATERN12, MATERN32, MATERN52, TANIMOTO, TANIMOTO_BITS = range(6)
+RBF, MATERN12, MATERN32, MATERN52, TANIMOTO, TANIMOTO_BITS, HAMMING_LUT = range(7)
 # constant folded into the lengthscale so that the kernels see  RBF = exp(-d2), Matern = f(r), r = sqrt(d2)
 FAMILY_SCALE = {RBF: 0.5 ** 0.5, MATERN12: 1.0, MATERN32: 3.0 ** 0.5, MATERN52: 5.0 ** 0.5, TANIMOTO: 1.0}
 BITS_MAX_D = 2048  # the popcount Tanimoto kernel covers fingerprints of up to 2048 bits
@@ -34,6 +34,7 @@ class GroupArgs(C.Structure):
         ("At", C.c_void_p), ("totw", C.c_void_p),
         ("variant", C.c_int32), ("unit_weights", C.c_int32),
         ("rec", C.c_void_p), ("ldr", C.c_int64),
+        ("lut", C.c_void_p),
     ]
 
 

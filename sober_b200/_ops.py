@@ -38,8 +38,9 @@ class LandmarkTable:
     """``Zt`` (L x d) and ``zn`` (L) as K1 wants them, plus the family / output scale.  ``d`` overrides the column
     count when the rows are bit-packed words (family TANIMOTO_BITS: d = number of bits)."""
 
-    def __init__(self, zt, zn, family, outputscale, d=None):
+    def __init__(self, zt, zn, family, outputscale, d=None, lut=None):
         self.zt, self.zn, self.family, self.outputscale = zt, zn, family, float(outputscale)
+        self.lut = lut          # family HAMMING_LUT: kernel value per Hamming distance (d + 1 doubles)
         self.L = zt.shape[0]
         self.d = zt.shape[1] if d is None else int(d)
 
@@ -189,6 +190,7 @@ class CudaOps:
         a.S, a.L, a.d, a.family = int(S), int(lm.L), int(lm.d), int(lm.family)
         a.outputscale = lm.outputscale
         a.Zt, a.zn = lm.zt.data_ptr(), lm.zn.data_ptr()
+        a.lut = None if lm.lut is None else lm.lut.data_ptr()
         a.At, a.totw = At.data_ptr(), totw.data_ptr()
         a.variant = self.variant
         nbytes = self.lib.sober_group_accumulate_workspace(C.byref(a))

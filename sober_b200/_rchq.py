@@ -80,6 +80,18 @@ class KeepMap:
         return self.E * self.K + ((p - self.ES) if self.tail_keep else 0)
 
 
+def _family_values(family, d2):
+    """Kernel value as a function of the (family-scaled) squared distance -- the formulas of csrc/common.cuh."""
+    if family == _lib.RBF:
+        return torch.exp(-d2)
+    r = d2.clamp_min(1e-30).sqrt()
+    if family == _lib.MATERN12:
+        return torch.exp(-r)
+    if family == _lib.MATERN32:
+        return (1 + r) * torch.exp(-r)
+    return (1 + r + d2.clamp_min(1e-30) / 3.0) * torch.exp(-r)
+
+
 class Alive:
     """This rank's part of the compact alive-list, in position order: row ids, weights and -- record layout --
     the record rows K1 streams."""
@@ -118,7 +130,8 @@ class Recombiner:
         self.nullspace = nullspace        # test hook: design -> (k x S) rows
         self.basis = basis                # test hook: use this Nystrom basis U (n x L) instead of computing it
         self.trace = trace                # test hook: trace(stage, dict) with per-iteration intermediates
-        self._bits = False                # set per call: Tanimoto on {0,1} rows -> bit-packed popcount kernel
+        self._bits = False                # set per call: "tanimoto" / "hamming" when {0,1} rows are bit-packed
+        self._lut = None                  # Hamming path: kernel value per Hamming distance
 
     # -----------------------------------------------------------------------------------------------------
     # landmarks / Nystrom block
@@ -128,8 +141,9 @@ class Recombiner:
         if self._bits:
             words, popc, ok = self.ops.pack_bits(pts)
             if not ok:
-                raise ValueError("non-binary landmark rows on the bit-packed Tanimoto path")
-            return LandmarkTable(words, popc, _lib.TANIMOTO_BITS, spec.outputscale, d=pts.shape[1])
+                raise ValueError("non-binary landmark rows on a bit-packed path")
+            fam = _lib.HAMMING_LUT if self._bits == "hamming" else _lib.TANIMOTO_BITS
+            return LandmarkTable(words, popc, fam, spec.outputscale, d=pts.shape[1], lut=self._lut)
         if spec.stationary:
             v = (pts - center) * inv_ls
             return LandmarkTable((-2.0 * v).contiguous(), (v * v).sum(-1).contiguous(), spec.family, spec.outputscale)
@@ -142,7 +156,7 @@ class Recombiner:
         if self._bits:
             words, popc, ok = self.ops.pack_bits(X)
             if not ok:
-                raise ValueError("non-binary rows on the bit-packed Tanimoto path")
+                raise ValueError("non-binary rows on a bit-packed path")
             return PointSet(words, words.stride(0), popc, 1, X.shape[0], X.shape[1])
         if self._use_records(spec, X.shape[1]):
             return self.ops.make_records(X, center, inv_ls)
@@ -243,19 +257,30 @@ class Recombiner:
         elif spec is not None:
             center = torch.zeros(d, dtype=torch.float64, device=dev)
             inv_ls = torch.ones(d, dtype=torch.float64, device=dev)
-        # Tanimoto on fingerprints: if every entry of the candidates and landmarks is 0/1 the rows are bit-packed once
-        # and <x, z> becomes popcount(x & z)  (64x less data, integer pipe instead of d FP64 FMAs per pair)
-        self._bits = False
+        # {0,1}-valued inputs: rows are bit-packed once (64x less data) and the contraction runs on the integer pipe.
+        #   Tanimoto: <x, z> = popcount(x & z);
+        #   stationary kernel with a single lengthscale (examples/ising.py: RBF on {0,1}^24): the squared distance is
+        #   the Hamming distance times a constant, so the kernel value is a (d + 1)-entry lookup table.
+        self._bits, self._lut = False, None
         cand_bits = None
-        if (spec is not None and spec.family == _lib.TANIMOTO and _lib.RECORD_MAX_D < d <= _lib.BITS_MAX_D
-                and o.k1_variant != 1 and hasattr(ops, "pack_bits")):
+        want = None
+        if spec is not None and _lib.RECORD_MAX_D < d <= _lib.BITS_MAX_D and o.k1_variant != 1 and hasattr(ops, "pack_bits"):
+            if spec.family == _lib.TANIMOTO:
+                want = "tanimoto"
+            elif spec.stationary and spec.inv_ls.numel() == 1:
+                want = "hamming"
+        if want is not None:
             zw, zp, z_ok = ops.pack_bits(Z)
             if z_ok and (spec.x_obs is None or ops.pack_bits(ops.f64(spec.x_obs))[2]):
                 xw, xp, x_ok = ops.pack_bits(X)
                 flags = comm.all_gather_ints(int(x_ok), dev)
                 if all(flags):
-                    self._bits = True
+                    self._bits = want
                     cand_bits = PointSet(xw, xw.stride(0), xp, 1, X.shape[0], d)
+                    if want == "hamming":
+                        step = (float(spec.inv_ls.reshape(-1)[0]) * _lib.FAMILY_SCALE[spec.family]) ** 2
+                        h = torch.arange(d + 1, dtype=torch.float64, device=dev)
+                        self._lut = _family_values(spec.family, h * step).contiguous()
         records = self._use_records(spec, d) and not self._bits
 
         clock.lap("setup")

@@ -32,6 +32,7 @@ struct GroupParams {
     int unit_weights;
     const double* Zt;
     const double* zn;
+    const double* lut;
     double* out;       // [nsplit][S][L]  (or At itself when nsplit == 1)
     double* totw_out;  // [nsplit][S]
     int64_t row_begin, row_end, rows_per_split;
@@ -340,8 +341,10 @@ __global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
 // instructions per pair instead of 1024 DFMAs.
 constexpr int BITS_ROWS = 8;   // rows per staged chunk
 
-template <int W, int TL, int TG>
+template <int W, int TL, int TG, bool LUT>
 __global__ void __launch_bounds__(256) group_bits_kernel(const GroupParams p) {
+    // LUT: stationary kernel on binary rows -- k = lut[popcount(x ^ z)]; else Tanimoto -- popcount(x & z) + ratio
+    extern __shared__ double lut_s[];                    // d + 1 entries (LUT only)
     __shared__ __align__(16) uint64_t xb[BITS_ROWS][TG][W];
     __shared__ double s_w[BITS_ROWS][TG], s_xn[BITS_ROWS][TG];
     __shared__ int64_t s_row[BITS_ROWS][TG];
@@ -352,6 +355,10 @@ __global__ void __launch_bounds__(256) group_bits_kernel(const GroupParams p) {
     const int g0 = blockIdx.x * TG;
     const int l0 = (blockIdx.y * 8 + warp) * (32 * TL);
     const bool active = l0 < p.L;
+    if (LUT) {
+        for (int h = t; h <= p.d; h += 256) lut_s[h] = p.lut[h];
+        // first use is after the block barriers of the staging loop below
+    }
 
     uint64_t zb[TL][W];
     double zn[TL];
@@ -432,12 +439,12 @@ __global__ void __launch_bounds__(256) group_bits_kernel(const GroupParams p) {
                     for (int w = 0; w < W; ++w) {
                         const uint64_t xw = xb[r][j][w];
 #pragma unroll
-                        for (int i = 0; i < TL; ++i) cnt[i] += __popcll(xw & zb[i][w]);
+                        for (int i = 0; i < TL; ++i) cnt[i] += __popcll(LUT ? (xw ^ zb[i][w]) : (xw & zb[i][w]));
                     }
                     const double xn = s_xn[r][j], wgt = s_w[r][j];
 #pragma unroll
                     for (int i = 0; i < TL; ++i) {
-                        const double kv = tanimoto_value((double)cnt[i], xn, zn[i]);
+                        const double kv = LUT ? lut_s[cnt[i]] : tanimoto_value((double)cnt[i], xn, zn[i]);
                         acc[i][j] = fma(kv, wgt, acc[i][j]);
                     }
                 }
@@ -527,7 +534,8 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
     pl->row_end = a->n_local > 0 ? ceil_div(hi, a->S) : pl->row_begin;
     const int64_t rows = pl->row_end - pl->row_begin;
     pl->records = a->rec != nullptr && a->variant != 1;
-    pl->bits = a->family == SOBER_TANIMOTO_BITS;
+    pl->bits = a->family == SOBER_TANIMOTO_BITS || a->family == SOBER_HAMMING_LUT;
+    if (a->family == SOBER_HAMMING_LUT && !a->lut) return false;
     if (pl->bits) {
         const int64_t W = a->ldx;
         if (pl->records || a->d <= 0 || W < (a->d + 63) / 64 || !(W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32))
@@ -581,14 +589,16 @@ static bool launch_records_d(const Plan& pl, const GroupParams& p, cudaStream_t 
     }
 }
 
+template <bool LUT>
 static bool launch_bits(const Plan& pl, const GroupParams& p, cudaStream_t st) {
+    const size_t sm = LUT ? (size_t)(p.d + 1) * 8 : 0;
     switch ((int)p.ldx) {
-        case 1: group_bits_kernel<1, 4, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
-        case 2: group_bits_kernel<2, 4, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
-        case 4: group_bits_kernel<4, 4, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
-        case 8: group_bits_kernel<8, 4, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
-        case 16: group_bits_kernel<16, 2, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
-        case 32: group_bits_kernel<32, 1, BITS_TG><<<pl.grid, pl.block, 0, st>>>(p); return true;
+        case 1: group_bits_kernel<1, 4, BITS_TG, LUT><<<pl.grid, pl.block, sm, st>>>(p); return true;
+        case 2: group_bits_kernel<2, 4, BITS_TG, LUT><<<pl.grid, pl.block, sm, st>>>(p); return true;
+        case 4: group_bits_kernel<4, 4, BITS_TG, LUT><<<pl.grid, pl.block, sm, st>>>(p); return true;
+        case 8: group_bits_kernel<8, 4, BITS_TG, LUT><<<pl.grid, pl.block, sm, st>>>(p); return true;
+        case 16: group_bits_kernel<16, 2, BITS_TG, LUT><<<pl.grid, pl.block, sm, st>>>(p); return true;
+        case 32: group_bits_kernel<32, 1, BITS_TG, LUT><<<pl.grid, pl.block, sm, st>>>(p); return true;
         default: return false;
     }
 }
@@ -617,7 +627,7 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
     if (!plan_group(a, &pl)) return SOBER_ERR_ARG;
     if (!a->Zt || !a->zn || !a->At || !a->totw) return SOBER_ERR_ARG;
     if (!pl.records && (!a->X || !a->xn)) return SOBER_ERR_ARG;
-    if (a->family < SOBER_RBF || a->family > SOBER_TANIMOTO_BITS) return SOBER_ERR_UNSUPPORTED;
+    if (a->family < SOBER_RBF || a->family > SOBER_HAMMING_LUT) return SOBER_ERR_UNSUPPORTED;
     const int64_t need = sober_group_accumulate_workspace(a);
     if (need > workspace_bytes || (need > 0 && !workspace)) return SOBER_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -635,7 +645,7 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
     p.n_local = a->n_local; p.pos0 = a->pos0; p.ES = a->ES;
     p.S = a->S; p.L = a->L; p.d = a->d;
     p.unit_weights = a->unit_weights;
-    p.Zt = a->Zt; p.zn = a->zn;
+    p.Zt = a->Zt; p.zn = a->zn; p.lut = a->lut;
     p.row_begin = pl.row_begin; p.row_end = pl.row_end; p.rows_per_split = pl.rows_per_split;
     double* ws = (double*)workspace;
     if (pl.nsplit == 1) {
@@ -654,7 +664,8 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
         case SOBER_MATERN32: ok = launch_family<SOBER_MATERN32>(pl, p, st); break;
         case SOBER_MATERN52: ok = launch_family<SOBER_MATERN52>(pl, p, st); break;
         case SOBER_TANIMOTO: ok = launch_family<SOBER_TANIMOTO>(pl, p, st); break;
-        case SOBER_TANIMOTO_BITS: ok = launch_bits(pl, p, st); break;
+        case SOBER_TANIMOTO_BITS: ok = launch_bits<false>(pl, p, st); break;
+        case SOBER_HAMMING_LUT: ok = launch_bits<true>(pl, p, st); break;
     }
     if (!ok) return SOBER_ERR_UNSUPPORTED;
     SOBER_LAUNCH_CHECK("group_accumulate");

@@ -12,7 +12,7 @@ import torch
 from oracle import rchq as oracle
 from sober_b200._ops import LandmarkTable, PointSet  # plain containers, no CUDA needed
 
-RBF, MATERN12, MATERN32, MATERN52, TANIMOTO, TANIMOTO_BITS = range(6)
+RBF, MATERN12, MATERN32, MATERN52, TANIMOTO, TANIMOTO_BITS, HAMMING_LUT = range(7)
 
 
 def kernel_values(dot, xn, zn, family):
@@ -85,7 +85,11 @@ class TorchOps:
             w = torch.ones(n_local, dtype=torch.float64) if mu is None else mu[:n_local]
             x = pts.rows[rows, :d]
             xn = pts.xn[rows].reshape(-1, 1)
-        kv = kernel_values(x @ lm.zt.T, xn, lm.zn.reshape(1, -1), lm.family) * w.reshape(-1, 1)
+        if lm.family == HAMMING_LUT:
+            ham = (xn + lm.zn.reshape(1, -1) - 2.0 * (x @ lm.zt.T)).round().long()
+            kv = lm.lut[ham] * w.reshape(-1, 1)
+        else:
+            kv = kernel_values(x @ lm.zt.T, xn, lm.zn.reshape(1, -1), lm.family) * w.reshape(-1, 1)
         pos = pos0 + torch.arange(n_local)
         at.index_add_(0, pos % S, kv)
         inside = pos < ES

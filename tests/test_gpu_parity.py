@@ -37,6 +37,22 @@ def scaled(spec, Z, dev):
     return torch.zeros(d, dtype=torch.float64, device=dev), torch.ones(d, dtype=torch.float64, device=dev)
 
 
+def enable_bits(rec, spec, d, dev):
+    """Select the bit-packed K1 path the way Recombiner.run does for {0,1} inputs with d > 8."""
+    from sober_b200 import _lib
+    from sober_b200._rchq import _family_values
+    rec._bits, rec._lut = False, None
+    if d <= _lib.RECORD_MAX_D:
+        return False
+    if spec.family == _lib.TANIMOTO:
+        rec._bits = "tanimoto"
+    elif spec.stationary and spec.inv_ls.numel() == 1:
+        rec._bits = "hamming"
+        step = (float(spec.inv_ls.reshape(-1)[0]) * _lib.FAMILY_SCALE[spec.family]) ** 2
+        rec._lut = _family_values(spec.family, torch.arange(d + 1, dtype=torch.float64, device=dev) * step).contiguous()
+    return bool(rec._bits)
+
+
 def spec_tables(rec, case, dev):
     """Landmark table / prepared points for a fixture, built the way Recombiner does."""
     from sober_b200._kernel_spec import introspect
@@ -54,13 +70,12 @@ def spec_tables(rec, case, dev):
 def test_gram_matches_oracle(ops, cuda_device, name, variant):
     from sober_b200 import Recombiner, configure
     case = Case(name, cuda_device)
-    if variant == 0 and case.X.shape[1] > 8 and case.fam != "tanimoto":
-        pytest.skip("register kernel covers d <= 8")
     with configure(k1_variant=variant) as opts:
         rec = Recombiner(ops, opts=opts)
         ops.variant = variant
         kern, spec, center, inv_ls = spec_tables(rec, case, cuda_device)
-        rec._bits = variant == 0 and case.fam == "tanimoto"          # bit-packed popcount kernel
+        if variant == 0:
+            enable_bits(rec, spec, case.X.shape[1], cuda_device)   # binary fixtures with d > 8: bit-packed kernels
         try:
             table = rec._table(case.Z, spec, center, inv_ls)
             got_zz = rec._gram_T(rec._points(case.Z, spec, center, inv_ls), table).T
@@ -107,8 +122,6 @@ def test_group_accumulate_matches_oracle_trace(ops, cuda_device, name, variant):
     case = Case(name)                                   # oracle on the CPU
     if case.objective is not None:
         pytest.skip("objective branch covered end-to-end")
-    if variant == 0 and case.X.shape[1] > 8 and case.fam != "tanimoto":
-        pytest.skip("register kernel covers d <= 8")
     groups, updates = [], []
 
     def trace(stage, payload):
@@ -132,7 +145,8 @@ def test_group_accumulate_matches_oracle_trace(ops, cuda_device, name, variant):
         with configure(k1_variant=variant) as opts:
             rec = Recombiner(ops, opts=opts, basis=dcase.U)
             kern, spec, center, inv_ls = spec_tables(rec, dcase, cuda_device)
-            rec._bits = variant == 0 and case.fam == "tanimoto"
+            if variant == 0:
+                enable_bits(rec, spec, dcase.X.shape[1], cuda_device)
             U, Uext, table = rec._nystrom(dcase.Z, case.b - 1, kern, spec, center, inv_ls)
             records = rec._use_records(spec, dcase.X.shape[1])
             st = {"spec": spec, "table": table, "pts": None if records else rec._points(dcase.X, spec, center, inv_ls)}
@@ -380,12 +394,31 @@ def test_tanimoto_popcount_gram_matches_oracle(ops, cuda_device, d, density):
     Z = X[torch.randperm(3000, generator=g)[:333].to(cuda_device)].clone()
     kern = ok.Kernel(ok.BareModel(ok.make_kernel("tanimoto", 1.0, 1.9).to(cuda_device)), mode="kernel")
     rec = Recombiner(ops)
-    rec._bits = True
+    rec._bits = "tanimoto"
     spec = introspect(kern)
     center, inv_ls = scaled(spec, Z, cuda_device)
     got = rec._gram_T(rec._points(X, spec, center, inv_ls), rec._table(Z, spec, center, inv_ls)).T
     want = kern(Z, X)
     assert rel(got, want) < 1e-13
+
+
+@pytest.mark.parametrize("fam,nu,d", [("rbf", None, 24), ("matern", 2.5, 24), ("matern", 1.5, 100), ("rbf", None, 640)])
+def test_hamming_lut_gram_matches_oracle(ops, cuda_device, fam, nu, d):
+    """Stationary kernels with one lengthscale on {0,1}^d: k = lut[popcount(x ^ z)] vs the oracle's float kernel."""
+    from sober_b200 import Recombiner
+    from sober_b200._kernel_spec import introspect
+    g = torch.Generator().manual_seed(d)
+    X = (torch.rand(2500, d, generator=g) < 0.5).to(torch.float64).to(cuda_device)
+    Z = X[torch.randperm(2500, generator=g)[:260].to(cuda_device)].clone()
+    cov = ok.ScaleKernel(ok.RBFKernel([3.0]) if fam == "rbf" else ok.MaternKernel(nu, [3.0]), 0.7).to(cuda_device)
+    kern = ok.Kernel(ok.BareModel(cov), mode="kernel")
+    spec = introspect(kern)
+    rec = Recombiner(ops)
+    assert enable_bits(rec, spec, d, cuda_device) and rec._bits == "hamming"
+    center, inv_ls = scaled(spec, Z, cuda_device)
+    got = rec._gram_T(rec._points(X, spec, center, inv_ls), rec._table(Z, spec, center, inv_ls)).T
+    want = kern(Z, X)
+    assert rel(got, want) < 1e-11
 
 
 @pytest.mark.parametrize("m,q", [(400, 200), (1000, 199), (37, 33), (513, 256), (8, 1)])
