@@ -212,6 +212,17 @@ int sober_update_compact(const int32_t* idx_in, const double* mu_in, int64_t n_l
 int sober_scatter_result(double* dst, int64_t n, const int64_t* idx, const double* w, int64_t m, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Projection onto the Nystrom basis + barycentres + design matrix (SOBER/_rchq.py:148-166, :229), FP64 tensor pipe:
+ *   design[g, 0] = 1;  design[g, 1 + j] = (sum_l (At[g,l] + [g == S-1] tail[l]) Uext[j,l]) / totw_out[g]
+ *   totw_out[g] = totw[g] + [g == S-1] tail_tw[0]
+ * At: S x Lp (lda), Uext: n x Lp (ldu) = [U | -U K_zX W], design: S x (n + 1) (ldd); tail (Lp) / tail_tw (1) may be
+ * NULL (no remainder); totw_out may be NULL.  mma.sync m8n8k4 f64 (DMMA) with the epilogue fused.
+ * ------------------------------------------------------------------------------------------------- */
+int sober_project_design(const double* At, int64_t lda, const double* tail, const double* totw, const double* tail_tw,
+                         const double* Uext, int64_t ldu, int32_t S, int32_t Lp, int32_t n, double* design, int64_t ldd,
+                         double* totw_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Small dense helper of the Cholesky-QR steps (Nystrom range finder, projector null space):
  *   solve X * R = Y for upper-triangular R (q x q row-major, q <= 256), Y and X m x q row-major (X may alias Y).
  * One warp per row, the row in registers.  Replaces torch.linalg.solve_triangular (cuBLAS trsm: ~0.1 ms per call at
@@ -225,6 +236,8 @@ int sober_trsm_right_upper(const double* Y, int64_t ldy, const double* R, int64_
  * Launches `blocks` x 256 threads, each doing iters * 8 dependent-chain DFMAs; flops = blocks*256*iters*16.
  * ------------------------------------------------------------------------------------------------- */
 int sober_fp64_probe(int32_t blocks, int64_t iters, double* sink, void* stream);
+/* FP64 tensor-pipe probe: blocks x 8 warps, each iters * 8 DMMA m8n8k4; flops = blocks * 8 * iters * 8 * 512. */
+int sober_dmma_probe(int32_t blocks, int64_t iters, double* sink, void* stream);
 
 #ifdef __cplusplus
 }

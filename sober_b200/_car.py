@@ -55,15 +55,17 @@ def projector_rows(design, thin_q=None, with_defect=False):
     return rows
 
 
-def caratheodory(ops, feats, mass, how, nullspace=None):
+def caratheodory(ops, feats, mass, how, nullspace=None, design=None):
     """feats (S x n), mass (S,) -> weights (S,) with zeros at eliminated points; preserves [1 feats]^T mass.
+    ``design`` = [1 | feats] may be passed instead of ``feats`` (the projection kernel emits it directly).
 
     Small problems (the whole state fits the distributed shared memory of one thread-block cluster) run as ONE
     kernel, ``sober_car_cluster``: QR + null space + elimination for ``how="qr"``, the elimination alone -- with the
     reference's exact arithmetic -- on a torch-SVD / injected basis otherwise.  Larger ones take the null space from
     torch.linalg and the persistent multi-CTA elimination kernel."""
-    ones = torch.ones((feats.shape[0], 1), dtype=feats.dtype, device=feats.device)
-    design = torch.cat([ones, feats], dim=1).contiguous()
+    if design is None:
+        ones = torch.ones((feats.shape[0], 1), dtype=feats.dtype, device=feats.device)
+        design = torch.cat([ones, feats], dim=1).contiguous()
     pts, dim = design.shape
     out = mass.clone().contiguous()
     if pts <= dim:

@@ -231,6 +231,22 @@ class CudaOps:
         self.launches += 1
         return (piv, steps) if want_pivots else None
 
+    def project_design(self, at, uext, totw, tail=None, tail_tw=None):
+        """[1 | ((At + tail on the last row) @ Uext^T) / totw'] and totw' (totw plus the tail mass on the last group):
+        projection, barycentres and the design matrix of the CAR step in one DMMA kernel."""
+        S, Lp = at.shape
+        n = uext.shape[0]
+        design = torch.empty((S, n + 1), dtype=torch.float64, device=self.device)
+        totw_out = torch.empty(S, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            t0 = self._begin("project_design")
+            check(self.lib.sober_project_design(_ptr(at), at.stride(0), _ptr(tail), _ptr(totw), _ptr(tail_tw), _ptr(uext),
+                                                uext.stride(0), S, Lp, n, _ptr(design), design.stride(0), _ptr(totw_out),
+                                                self._stream()), "project_design")
+            self._end("project_design", t0, 2 * S * Lp * n)
+        self.launches += 1
+        return design, totw_out
+
     def car_cluster_fits(self, S, n_prime, have_basis):
         """Cluster size the fused CAR kernel would use for this shape, 0 if it does not fit in distributed smem."""
         with torch.cuda.device(self.device):

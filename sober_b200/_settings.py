@@ -33,7 +33,8 @@ class Options:
         self.set_mode(mode or os.environ.get("SOBER_B200_MODE", "fast"))
         self.fuse = True              # introspect Kernel objects; False forces the generic-callable path
         self.generic_chunk = 1 << 16  # candidates per Gram tile on the generic path
-        self.k1_variant = 0           # 0 auto, 1 tiled, 2 small-d register kernel
+        self.k1_variant = 0           # 0 auto (record / bit-packed kernels when they apply), 1 force the tiled kernel
+        self.fused_projection = False  # hand-written DMMA projection+barycentre kernel instead of cuBLAS DGEMM
         self.stats = None             # optional dict that receives per-stage timings (forces syncs)
 
     def set_mode(self, mode):

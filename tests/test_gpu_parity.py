@@ -437,6 +437,27 @@ def test_trsm_right_upper(ops, cuda_device, m, q):
     assert rel(solve_right_upper(low.mH, y), want) < 1e-11
 
 
+@pytest.mark.parametrize("S,Lp,n", [(400, 1000, 199), (48, 96, 23), (200, 530, 99), (33, 7, 5), (2000, 300, 999)])
+def test_project_design_dmma(ops, cuda_device, S, Lp, n):
+    """Projection + tail + barycentres + ones column (DMMA kernel) vs the same in torch."""
+    g = torch.Generator().manual_seed(S + Lp + n)
+    at = torch.randn(S, Lp, dtype=torch.float64, generator=g).to(cuda_device)
+    uext = torch.randn(n, Lp, dtype=torch.float64, generator=g).to(cuda_device)
+    totw = (torch.rand(S, dtype=torch.float64, generator=g) + 0.5).to(cuda_device)
+    tail = torch.randn(Lp, dtype=torch.float64, generator=g).to(cuda_device)
+    tail_tw = torch.tensor([0.37], dtype=torch.float64, device=cuda_device)
+    design, tw = ops.project_design(at, uext, totw, tail=tail, tail_tw=tail_tw)
+    at2 = at.clone()
+    at2[S - 1] += tail
+    tw2 = totw.clone()
+    tw2[S - 1] += 0.37
+    want = torch.cat([torch.ones(S, 1, dtype=torch.float64, device=cuda_device), (at2 @ uext.T) / tw2.unsqueeze(1)], 1)
+    assert torch.equal(tw, tw2)
+    assert rel(design, want) < 1e-12
+    design0, tw0 = ops.project_design(at, uext, totw)
+    assert torch.equal(tw0, totw) and rel(design0[:, 1:], (at @ uext.T) / totw.unsqueeze(1)) < 1e-12
+
+
 def test_scatter_result(ops, cuda_device):
     dst = torch.rand(1000, dtype=torch.float64, device=cuda_device)
     idx = torch.tensor([3, 17, 999], device=cuda_device)
