@@ -61,11 +61,16 @@ def synth(name, n, seed, device, generator_device=None):
     return X, mu
 
 
-def make_kernel(name, device):
+def make_kernel(name, device, pred_cov=False):
     from oracle import kernels as ok       # kernel OBJECTS only (gpytorch stand-ins); the product introspects them
     _, d, L, b, fam, ls, _ = WORKLOADS[name]
     cov = ok.make_kernel(fam, [ls] if ls is not None else 1.0, 1.0).to(device)
-    return ok.Kernel(ok.BareModel(cov), mode="kernel")
+    if not pred_cov:
+        return ok.Kernel(ok.BareModel(cov), mode="kernel")
+    # the default Sober kernel: GP posterior predictive covariance with a synthetic GP of 200 observations
+    g = torch.Generator().manual_seed(5)
+    x_obs = synth(name, 200, 5, torch.device("cpu"))[0].to(device)
+    return ok.Kernel(ok.GPModel(cov, x_obs, None, noise=1e-4), mode="predictive_covariance")
 
 
 class ClockSampler:
@@ -142,6 +147,8 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--cpu-sample", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pred-cov", action="store_true",
+                    help="use Kernel(model, 'predictive_covariance') with a synthetic 200-observation GP (SURVEY 8d)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,7 +200,7 @@ def main():
     Z = X[torch.randperm(n_local, device=dev, generator=torch.Generator(device=dev).manual_seed(1))[:L]].clone()
     if world > 1:
         dist.broadcast(Z, 0)
-    kern = make_kernel(name, dev)
+    kern = make_kernel(name, dev, args.pred_cov)
     from sober_b200 import _rchq
     ops = _rchq._ops()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
@@ -314,7 +321,8 @@ def main():
         "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": desc, "n_rec_total": n_total, "n_rec_per_gpu": n_local, "n_nys": L, "batch": b,
-                   "kernel": fam, "d": d, "mode": args.mode, "l2": "256 MiB buffer written between steps (flush)",
+                   "kernel": fam + (" / predictive_covariance (n_obs=200)" if args.pred_cov else " / kernel mode"),
+                   "d": d, "mode": args.mode, "l2": "256 MiB buffer written between steps (flush)",
                    "parallelism": "row-sharded candidates x%d" % world},
         "e2e": {"value": n_total * e_steps / (e2e_ms * 1e-3), "unit": "candidates/s", "ms_per_step": e2e_ms / e_steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -93,11 +93,19 @@ def _left_singular_vectors(b, max_sweeps=12, tol=1e-13):
         size = x.abs().max()
         x = x.clamp(-0.25, 0.25)
         u = u + u @ x                                     # U (I + X), X skew-symmetric to first order
-        chol, info = torch.linalg.cholesky_ex(u.mH @ u)   # re-orthonormalise (one Cholesky-QR pass)
-        status = torch.stack([info.to(torch.float64).reshape(()), size.to(torch.float64).reshape(())]).tolist()
-        if status[0] != 0:
-            break
-        u = solve_right_upper(chol.mH, u)
+        # re-orthonormalise: U^T U = I + D with D = O(|X|^2).  Small rotations: (I + D)^-1/2 = I - D/2 + 3 D^2/8 by
+        # GEMMs alone (error |D|^3); large ones (first sweeps of a badly seeded problem): one Cholesky-QR pass
+        status = size.to(torch.float64).reshape(1).tolist()          # the one host sync of the sweep
+        if status[0] < 1e-3:
+            d = u.mH @ u
+            d.diagonal().sub_(1.0)
+            u = u - 0.5 * (u @ d) + 0.375 * (u @ (d @ d))
+        else:
+            chol, info = torch.linalg.cholesky_ex(u.mH @ u)
+            if int(info) != 0:
+                break
+            u = solve_right_upper(chol.mH, u)
+        status = [0.0, status[0]]
         # converged, or stagnated at the noise floor eps * cond(b) / relgap of the closest pair (clustered spectrum):
         # the Jacobi SVD has the same intrinsic sensitivity there
         stalled = sweep >= 2 and status[1] < 1e-5 and status[1] > 0.25 * prev
