@@ -231,6 +231,14 @@ int sober_project_design(const double* At, int64_t lda, const double* tail, cons
 int sober_trsm_right_upper(const double* Y, int64_t ldy, const double* R, int64_t ldr, int32_t m, int32_t q, double* X,
                            int64_t ldx, void* stream);
 
+/* Cholesky factorisation G = R^T R of a symmetric positive definite q x q matrix (row-major, q <= 224; the upper
+ * triangle of G is read), R upper triangular with zeros below the diagonal.  One 2-CTA cluster, the triangle in
+ * registers, columns handed over through a shared-memory ring / bulk DSMEM copies (csrc/chol_pair.cu).  Replaces
+ * torch.linalg.cholesky_ex (cuSOLVER potrf: ~0.13 ms at q = 200).  *info (device) = 0, or 1 + the first column whose
+ * pivot was not positive (R is then NaN from that column on), as LAPACK reports it. */
+int sober_cholesky_upper_fits(int32_t q);
+int sober_cholesky_upper(const double* G, int64_t ldg, int32_t q, double* R, int64_t ldr, int32_t* info, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Diagnostics: FP64 FMA throughput probe (the roofline denominator for K1, which is FP64-pipe bound).
  * Launches `blocks` x 256 threads, each doing iters * 8 dependent-chain DFMAs; flops = blocks*256*iters*16.

@@ -33,7 +33,7 @@ def projector_rows(design, thin_q=None, with_defect=False):
     (error |Delta|^3) -- three small GEMMs instead of a second Cholesky + triangular solve.  ``with_defect`` also
     returns |Delta|_F (a device scalar) so that the caller can fall back when it is not small.  The projector does not
     see how Q1 was orthonormalised: a Householder Q1 gives the same matrix (what the oracle-side check uses)."""
-    from ._linalg import solve_right_upper
+    from ._linalg import cholesky_upper, solve_right_upper
     pts, dim = design.shape
     eye_k = torch.eye(pts - dim, dtype=design.dtype, device=design.device)
     if thin_q is not None:
@@ -41,8 +41,8 @@ def projector_rows(design, thin_q=None, with_defect=False):
         rows[:, dim:] += eye_k
         return rows.contiguous()
     scaled = design / design.norm(dim=0, keepdim=True).clamp_min(1e-300)
-    chol, _ = torch.linalg.cholesky_ex(scaled.mH @ scaled)          # no host sync: NaNs surface in the caller's check
-    qt = solve_right_upper(chol.mH, scaled)
+    r, _ = cholesky_upper(scaled.mH @ scaled)                       # no host sync: NaNs surface in the caller's check
+    qt = solve_right_upper(r, scaled)
     delta = qt.mH @ qt
     delta.diagonal().sub_(1.0)
     inv = delta @ delta - delta

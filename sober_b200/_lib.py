@@ -68,6 +68,8 @@ PROTOTYPES = {
     "sober_project_design": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
     "sober_trsm_right_upper": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _I64, _P]),
     "sober_fp64_probe": (C.c_int, [_I32, _I64, _P, _P]),
+    "sober_cholesky_upper_fits": (C.c_int, [_I32]),
+    "sober_cholesky_upper": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _P]),
     "sober_dmma_probe": (C.c_int, [_I32, _I64, _P, _P]),
 }
 

@@ -1,7 +1,8 @@
 """Small dense helpers shared by the Nystrom range finder and the projector null space.
 
-(The q x q Cholesky factorisations stay with ``torch.linalg.cholesky_ex``: a hand-written one-CTA kernel was 3x slower
-than cuSOLVER's potrf at q = 200.)
+``cholesky_upper(g)`` returns ``(r, info)`` with ``r^T r = g``, r upper triangular.  On a CUDA float64 matrix with
+q <= 224 it is the register-resident 2-CTA cluster kernel of ``csrc/chol_pair.cu``; otherwise
+``torch.linalg.cholesky_ex`` (cuSOLVER potrf, ~0.13 ms at q = 200).  ``info`` is a device scalar (no host sync).
 
 ``solve_right_upper(r, y)`` solves ``X @ r = y`` for upper-triangular ``r``.  On a CUDA tensor with q <= 256 it calls
 the hand-written warp-per-row kernel (``csrc/small_linalg.cu``); otherwise (CPU tensors in the host-logic tests,
@@ -11,6 +12,27 @@ import ctypes as C
 import torch
 
 from . import _lib
+
+launches = 0   # kernels launched from this module (bench.py adds them to its gpu_launches claim)
+
+
+def cholesky_upper(g):
+    q = g.shape[-1]
+    if g.is_cuda and g.dtype == torch.float64 and g.dim() == 2 and 0 < q <= 224:
+        lib = _lib.load()
+        g = g.contiguous()
+        r = torch.empty_like(g)
+        info = torch.empty((), dtype=torch.int32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(lib.sober_cholesky_upper(
+                C.c_void_p(g.data_ptr()), g.stride(0), q, C.c_void_p(r.data_ptr()), r.stride(0),
+                C.c_void_p(info.data_ptr()), C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)),
+                "cholesky_upper")
+        global launches
+        launches += 1
+        return r, info
+    chol, info = torch.linalg.cholesky_ex(g)
+    return chol.mH, info
 
 
 def solve_right_upper(r, y):
@@ -25,5 +47,7 @@ def solve_right_upper(r, y):
                 C.c_void_p(y.data_ptr()), y.stride(0), C.c_void_p(r.data_ptr()), r.stride(0), y.shape[0], q,
                 C.c_void_p(out.data_ptr()), out.stride(0), C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)),
                 "trsm_right_upper")
+        global launches
+        launches += 1
         return out
     return torch.linalg.solve_triangular(r, y, upper=True, left=False)

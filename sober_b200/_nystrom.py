@@ -5,7 +5,7 @@ through the randomised range finder of ``torch.svd_lowrank`` (Halko et al. alg. 
 """
 import torch
 
-from ._linalg import solve_right_upper
+from ._linalg import cholesky_upper, solve_right_upper
 
 # Tests can set this to inject a test matrix drawn elsewhere (e.g. on the CPU generator the oracle used).
 _injected_test_matrix = None
@@ -19,7 +19,7 @@ def draw_test_matrix(rows, cols, dtype, device):
     return torch.randn(rows, cols, dtype=dtype, device=device)
 
 
-def _orthonormal_basis(y, how, check=True):
+def _orthonormal_basis(y, how, check=True, passes=2):
     """Q of the thin QR of y (m x q, m >= q).
 
     ``householder``: torch.linalg.qr (cuSOLVER geqrf + orgqr: ~1.2 ms for 1000 x 199 on B200, an unblocked panel
@@ -27,16 +27,17 @@ def _orthonormal_basis(y, how, check=True):
     triangular solves; mathematically the same Q up to column signs (the QR factorisation of a full-rank matrix is
     unique up to signs, and the final basis U = Q svd(Q^T K).U does not see them), numerically orthonormal to
     rounding while cond(y) < ~1e8.  Falls back to Householder when a Cholesky factorisation breaks down
-    (numerically rank-deficient y, e.g. a low-dimensional RBF Gram)."""
+    (numerically rank-deficient y, e.g. a low-dimensional RBF Gram).  ``passes=1`` leaves Q orthonormal only to
+    eps * cond(y)^2 -- enough for the intermediate bases of the power iteration, which exist for stability alone."""
     if how == "cholqr2" and y.shape[0] >= y.shape[1]:
         q = y
-        for _ in range(2):
+        for _ in range(passes):
             gram = q.mH @ q
-            chol, info = torch.linalg.cholesky_ex(gram)
+            r, info = cholesky_upper(gram)
             # check=False: no host sync; a breakdown leaves NaNs that the caller detects downstream
             if check and int(info) != 0:
                 return torch.linalg.qr(y).Q
-            q = solve_right_upper(chol.mH, q)
+            q = solve_right_upper(r, q)
         return q
     return torch.linalg.qr(y).Q
 
@@ -53,10 +54,13 @@ def lowrank_basis(gram, rank, niter=2, qr="householder"):
         return -1 * left.T
     size = gram.shape[-1]
     probe = draw_test_matrix(size, rank, gram.dtype, gram.device)
-    q = _orthonormal_basis(gram @ probe, qr)
-    for _ in range(niter):
-        q = _orthonormal_basis(gram.mH @ q, qr)
-        q = _orthonormal_basis(gram @ q, qr)
+    # range(Q) after the last orthonormalisation is range(K (K^T K)^niter Omega) whatever the intermediate bases
+    # were: those only keep the columns from collapsing onto the dominant eigenvector, for which one Cholesky-QR
+    # pass (orthonormal to eps cond^2) does as well as two.  The last basis is orthonormalised to rounding.
+    q = _orthonormal_basis(gram @ probe, qr, passes=1 if niter > 0 else 2)
+    for it in range(niter):
+        q = _orthonormal_basis(gram.mH @ q, qr, passes=1)
+        q = _orthonormal_basis(gram @ q, qr, passes=2 if it == niter - 1 else 1)
     small = q.mH @ gram                                   # B = Q^T K  (q x L)
     if qr == "cholqr2" and small.shape[0] <= small.shape[1]:
         u_small = _left_singular_vectors(small)
@@ -101,10 +105,10 @@ def _left_singular_vectors(b, max_sweeps=12, tol=1e-13):
             d.diagonal().sub_(1.0)
             u = u - 0.5 * (u @ d) + 0.375 * (u @ (d @ d))
         else:
-            chol, info = torch.linalg.cholesky_ex(u.mH @ u)
+            r, info = cholesky_upper(u.mH @ u)
             if int(info) != 0:
                 break
-            u = solve_right_upper(chol.mH, u)
+            u = solve_right_upper(r, u)
         status = [0.0, status[0]]
         # converged, or stagnated at the noise floor eps * cond(b) / relgap of the closest pair (clustered spectrum):
         # the Jacobi SVD has the same intrinsic sensitivity there

@@ -437,6 +437,47 @@ def test_trsm_right_upper(ops, cuda_device, m, q):
     assert rel(solve_right_upper(low.mH, y), want) < 1e-11
 
 
+@pytest.mark.parametrize("q", [1, 2, 31, 32, 33, 64, 65, 100, 160, 199, 200, 224])
+def test_cholesky_upper_cluster_kernel(ops, cuda_device, q):
+    """2-CTA register-resident Cholesky (csrc/chol_pair.cu) vs LAPACK: same factor to rounding, R^T R = G, exact zeros
+    below the diagonal, info = 0."""
+    from sober_b200._linalg import cholesky_upper
+    g = torch.Generator().manual_seed(q)
+    a = torch.randn(2 * q + 3, q, dtype=torch.float64, generator=g)
+    gram = a.T @ a
+    want = torch.linalg.cholesky(gram).T
+    r, info = cholesky_upper(gram.to(cuda_device))
+    assert int(info) == 0
+    assert torch.equal(torch.tril(r, -1), torch.zeros_like(r))
+    assert rel(r.cpu(), want) < 1e-12
+    assert rel((r.T @ r).cpu(), gram) < 1e-14
+    # padded leading dimension (a view into a wider matrix)
+    wide = torch.zeros(q, q + 7, dtype=torch.float64, device=cuda_device)
+    wide[:, :q] = gram.to(cuda_device)
+    from sober_b200 import _lib
+    import ctypes as C
+    out = torch.full((q, q + 3), 7.0, dtype=torch.float64, device=cuda_device)
+    inf2 = torch.ones((), dtype=torch.int32, device=cuda_device)
+    _lib.check(_lib.load().sober_cholesky_upper(C.c_void_p(wide.data_ptr()), q + 7, q, C.c_void_p(out.data_ptr()), q + 3,
+                                                C.c_void_p(inf2.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream().cuda_stream)), "chol")
+    assert int(inf2) == 0 and torch.equal(out[:, :q], r) and bool((out[:, q:] == 7.0).all())
+
+
+@pytest.mark.parametrize("q,bad", [(200, 137), (64, 0), (33, 32), (100, 99)])
+def test_cholesky_upper_reports_first_bad_pivot(ops, cuda_device, q, bad):
+    """Not positive definite: info = 1 + first failing column (LAPACK's convention), NaN from that column on."""
+    from sober_b200._linalg import cholesky_upper
+    g = torch.Generator().manual_seed(q + bad)
+    a = torch.randn(2 * q, q, dtype=torch.float64, generator=g)
+    gram = a.T @ a
+    gram[bad, bad] = -1.0 if bad == 0 else gram[bad, bad] - 1e6
+    _, want_info = torch.linalg.cholesky_ex(gram)
+    r, info = cholesky_upper(gram.to(cuda_device))
+    assert int(info) == int(want_info) == bad + 1
+    assert bool(torch.isnan(r[bad, bad])) and bool(torch.isfinite(r[:bad]).all())
+
+
 @pytest.mark.parametrize("S,Lp,n", [(400, 1000, 199), (48, 96, 23), (200, 530, 99), (33, 7, 5), (2000, 300, 999)])
 def test_project_design_dmma(ops, cuda_device, S, Lp, n):
     """Projection + tail + barycentres + ones column (DMMA kernel) vs the same in torch."""

@@ -1,3 +1,5 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, time
 dev = torch.device("cuda")
 def bench(name, fn, n=20):
@@ -17,6 +19,12 @@ for L, q in [(1000, 199), (2000, 999)]:
     bench("K @ R (LxL @ Lxq)", lambda: K @ R)
     bench("Y^T Y", lambda: Y.T @ Y)
     bench("cholesky_ex(q)", lambda: torch.linalg.cholesky_ex(G))
+    if q <= 224:
+        from sober_b200._linalg import cholesky_upper, solve_right_upper
+        bench("cholesky_upper (2-CTA cluster kernel)", lambda: cholesky_upper(G), n=200)
+        bench("cholesky_ex(q) x200", lambda: torch.linalg.cholesky_ex(G), n=200)
+        Rr = cholesky_upper(G)[0]
+        bench("solve_right_upper (Lxq)", lambda: solve_right_upper(Rr, Y), n=200)
     bench("cholesky_ex(q) + int(info) sync", lambda: int(torch.linalg.cholesky_ex(G)[1]))
     bench("cholesky_ex(L)", lambda: torch.linalg.cholesky_ex(K))
     bench("solve_triangular right (Lxq)", lambda: torch.linalg.solve_triangular(C.mH, Y, upper=True, left=False))
