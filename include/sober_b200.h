@@ -225,7 +225,8 @@ int sober_project_design(const double* At, int64_t lda, const double* tail, cons
 /* ---------------------------------------------------------------------------------------------------
  * Small dense helper of the Cholesky-QR steps (Nystrom range finder, projector null space):
  *   solve X * R = Y for upper-triangular R (q x q row-major, q <= 256), Y and X m x q row-major (X may alias Y).
- * One warp per row, the row in registers.  Replaces torch.linalg.solve_triangular (cuBLAS trsm: ~0.1 ms per call at
+ * R must be 16-byte aligned with ldr <= 384 (its 16-row tiles are TMA bulk copies), else SOBER_ERR_UNSUPPORTED.
+ * One warp per two rows, the rows in registers.  Replaces torch.linalg.solve_triangular (cuBLAS trsm: ~0.1 ms per call at
  * q = 200, called ~40 times per recombination).
  * ------------------------------------------------------------------------------------------------- */
 int sober_trsm_right_upper(const double* Y, int64_t ldy, const double* R, int64_t ldr, int32_t m, int32_t q, double* X,

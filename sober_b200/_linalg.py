@@ -40,6 +40,8 @@ def solve_right_upper(r, y):
     if y.is_cuda and y.dtype == torch.float64 and q <= 256 and y.dim() == 2:
         lib = _lib.load()
         r = r.contiguous()
+        if r.data_ptr() % 16:
+            r = r.clone()              # the kernel fetches R with TMA bulk copies (16-byte aligned base)
         y = y.contiguous()
         out = torch.empty_like(y)
         with torch.cuda.device(y.device):

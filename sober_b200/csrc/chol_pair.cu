@@ -289,7 +289,13 @@ extern "C" int sober_cholesky_upper(const double* G, int64_t ldg, int32_t n, dou
                                     void* stream) {
     if (!G || !R || !info || n <= 0 || n > CP_NMAX || ldg < n || ldr < n) return SOBER_ERR_ARG;
     const size_t smem = (size_t)CP_RING * CP_NMAX * sizeof(double) + (size_t)CP_NMAX * (sizeof(uint64_t) + sizeof(int));
-    SOBER_CUDA_CHECK(cudaFuncSetAttribute(chol_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool configured[64] = {};   // the > 48 KB opt-in is per device and sticky
+    int dev = 0;
+    SOBER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        SOBER_CUDA_CHECK(cudaFuncSetAttribute(chol_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
     CholParams p{G, (long long)ldg, R, (long long)ldr, info, n};
     chol_pair_kernel<<<2, CP_THREADS, smem, (cudaStream_t)stream>>>(p);
     SOBER_LAUNCH_CHECK("cholesky_upper");
