@@ -241,6 +241,14 @@ int sober_cholesky_upper_fits(int32_t q);
 int sober_cholesky_upper(const double* G, int64_t ldg, int32_t q, double* R, int64_t ldr, int32_t* info, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Stream confined to all SMs of the current device but `reserve_sms` (a CUDA green context; created on first use,
+ * cached, never destroyed).  Work launched on it leaves the reserved SMs to the other streams: the first K1 pass runs
+ * there beside the one-CTA kernels of the Nystrom range finder.  *stream = NULL when the driver cannot partition the
+ * device (still SOBER_OK): do not overlap then.  *sm_count = SMs of the partition.
+ * ------------------------------------------------------------------------------------------------- */
+int sober_partition_stream(int32_t reserve_sms, void** stream, int32_t* sm_count);
+
+/* ---------------------------------------------------------------------------------------------------
  * Diagnostics: FP64 FMA throughput probe (the roofline denominator for K1, which is FP64-pipe bound).
  * Launches `blocks` x 256 threads, each doing iters * 8 dependent-chain DFMAs; flops = blocks*256*iters*16.
  * ------------------------------------------------------------------------------------------------- */

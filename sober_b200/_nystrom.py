@@ -19,6 +19,45 @@ def draw_test_matrix(rows, cols, dtype, device):
     return torch.randn(rows, cols, dtype=dtype, device=device)
 
 
+class SideStream:
+    """Runs independent bulk work beside a host-driven sequence of small kernels.
+
+    ``with SideStream(launch, device, bulk_stream):`` -- on entry ``launch()`` is called with ``bulk_stream`` current
+    (after making it wait for everything enqueued so far); it returns the tensors it produced.  The body then runs on
+    the original stream; on exit that stream waits for the bulk work.  ``bulk_stream`` is confined to all SMs but a
+    few (``sober_partition_stream``, a CUDA green context), so the body's kernels always find free SMs.  (Two ordinary
+    streams do not overlap here, whatever their priorities: the bulk kernel's CTAs retire in waves ~0.4 ms apart and a
+    small kernel only gets an SM then -- measured.)"""
+
+    debug = None   # set to a list to collect {bulk_end, body_end} in ms after the fork (forces a sync)
+
+    def __init__(self, launch, device, bulk_stream):
+        self.launch, self.device, self.bulk = launch, device, bulk_stream
+
+    def __enter__(self):
+        self.main = torch.cuda.current_stream(self.device)
+        timing = SideStream.debug is not None
+        ready = torch.cuda.Event(enable_timing=timing)
+        ready.record(self.main)
+        self.bulk.wait_event(ready)
+        with torch.cuda.stream(self.bulk):
+            for t in self.launch():
+                t.record_stream(self.main)          # allocated on the bulk stream, consumed on the main one
+            if timing:
+                self.ev = [ready, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+                self.ev[1].record(self.bulk)
+        return self
+
+    def __exit__(self, *exc):
+        if SideStream.debug is not None:
+            self.ev[2].record(self.main)
+            torch.cuda.synchronize(self.device)
+            SideStream.debug.append({"bulk_end": self.ev[0].elapsed_time(self.ev[1]),
+                                     "body_end": self.ev[0].elapsed_time(self.ev[2])})
+        self.main.wait_stream(self.bulk)
+        return False
+
+
 def _orthonormal_basis(y, how, check=True, passes=2):
     """Q of the thin QR of y (m x q, m >= q).
 
@@ -42,13 +81,19 @@ def _orthonormal_basis(y, how, check=True, passes=2):
     return torch.linalg.qr(y).Q
 
 
-def lowrank_basis(gram, rank, niter=2, qr="householder"):
+def lowrank_basis(gram, rank, niter=2, qr="householder", rotate=True):
     """-(Q @ svd(Q^T K).U)^T of torch.svd_lowrank, with the same single random draw.
 
     ``qr="householder"`` and no injected test matrix: ``torch.svd_lowrank`` itself (parity mode).  Otherwise the same
     sequence spelled out, with the orthonormalisations by ``_orthonormal_basis`` and the final SVD taken on the
     triangular factor of (Q^T K)^T (left singular vectors of B = right singular vectors of R when B^T = Q_B R):
-    q x q instead of q x L Jacobi rotations."""
+    q x q instead of q x L Jacobi rotations.
+
+    ``rotate=False`` returns Q^T itself, without the q x q rotation by the left singular vectors of Q^T K: the rows span
+    the same space (the rotation is orthogonal and complete -- no singular vector is dropped, q = rank), which is all
+    that the recombination sees when its null spaces come from the orthogonal projector (``_car.projector_rows`` is a
+    function of range([1 | features]) alone; the terminal branches and the objective step likewise).  The rotation is
+    the most expensive N-independent item of the call (eigh + refinement: 2.7 ms of 20 at BASELINE configs[1])."""
     if _injected_test_matrix is None and qr == "householder":
         left, _, _ = torch.svd_lowrank(gram, q=rank, niter=niter)
         return -1 * left.T
@@ -57,10 +102,13 @@ def lowrank_basis(gram, rank, niter=2, qr="householder"):
     # range(Q) after the last orthonormalisation is range(K (K^T K)^niter Omega) whatever the intermediate bases
     # were: those only keep the columns from collapsing onto the dominant eigenvector, for which one Cholesky-QR
     # pass (orthonormal to eps cond^2) does as well as two.  The last basis is orthonormalised to rounding.
-    q = _orthonormal_basis(gram @ probe, qr, passes=1 if niter > 0 else 2)
+    last = 2 if rotate else 1                              # without the rotation only span(Q) matters
+    q = _orthonormal_basis(gram @ probe, qr, passes=1 if niter > 0 else last)
     for it in range(niter):
         q = _orthonormal_basis(gram.mH @ q, qr, passes=1)
-        q = _orthonormal_basis(gram @ q, qr, passes=2 if it == niter - 1 else 1)
+        q = _orthonormal_basis(gram @ q, qr, passes=last if it == niter - 1 else 1)
+    if not rotate:
+        return q.T.contiguous()
     small = q.mH @ gram                                   # B = Q^T K  (q x L)
     if qr == "cholqr2" and small.shape[0] <= small.shape[1]:
         u_small = _left_singular_vectors(small)

@@ -5,6 +5,7 @@ otherwise (no CPU fallback).  Tensors are allocated by torch (caching allocator)
 torch's current stream; nothing here synchronises except where a count has to reach the host.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -308,6 +309,21 @@ class CudaOps:
             check(self.lib.sober_scatter_result(_ptr(dst), dst.numel(), _ptr(idx), _ptr(w), idx.numel(),
                                                 self._stream()), "scatter_result")
         self.launches += 1
+
+    def partition_stream(self):
+        """Stream confined to all SMs but ``SOBER_B200_RESERVE_SMS`` (default 8), or None when the driver cannot
+        partition the device (include/sober_b200.h: sober_partition_stream)."""
+        if not hasattr(self, "_partition"):
+            reserve = int(os.environ.get("SOBER_B200_RESERVE_SMS", "8"))
+            self._partition = None
+            if reserve > 0:
+                ptr, sms = C.c_void_p(), C.c_int32()
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.sober_partition_stream(reserve, C.byref(ptr), C.byref(sms)), "partition_stream")
+                if ptr.value:
+                    self._partition = torch.cuda.ExternalStream(ptr.value, device=self.device)
+                    self.partition_sms = int(sms.value)
+        return self._partition
 
     def fp64_probe(self, blocks, iters):
         sink = torch.zeros(1, dtype=torch.float64, device=self.device)

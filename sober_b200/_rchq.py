@@ -20,6 +20,8 @@ and the only collective per iteration is one all-reduce of the (S x L') accumula
 import itertools
 import time
 
+import contextlib
+
 import torch
 
 from . import _car, _lib, _nystrom, _psd
@@ -169,37 +171,47 @@ class Recombiner:
                                           unit_weights=True)
         return at
 
-    def _nystrom(self, Z, n_basis, kernel, spec, center, inv_ls):
-        """-> U (n x L), Uext (n x L'), landmark table over L' = L (+ n_obs) stacked landmarks."""
-        o = self.opts
-        table = uext_tail = None
-        k_zo_w = None
+    def _landmarks(self, Z, spec, center, inv_ls):
+        """Landmark table over L' = L (+ n_obs) stacked landmarks, and the pieces of the predictive-covariance
+        correction (SOBER/_kernel.py:35-53): everything the K1 passes need that does not depend on the basis."""
+        lm = {"table": None, "table_z": None, "k_oz": None, "k_zo_w": None}
         if spec is not None:
-            table_z = self._table(Z, spec, center, inv_ls)
-            table = table_z
+            lm["table_z"] = lm["table"] = self._table(Z, spec, center, inv_ls)
             if spec.mode == "predictive_covariance":
                 x_obs = self.ops.f64(spec.x_obs)
                 w = self.ops.f64(spec.woodbury)
-                k_oz = self._gram_T(self._points(x_obs, spec, center, inv_ls), table_z)     # (n_obs x L)
-                k_zo_w = k_oz.T @ w                                                          # (L x n_obs)
-                table = self._table(torch.cat([Z, x_obs], 0), spec, center, inv_ls)
+                lm["k_oz"] = self._gram_T(self._points(x_obs, spec, center, inv_ls), lm["table_z"])   # (n_obs x L)
+                lm["k_zo_w"] = lm["k_oz"].T @ w                                                       # (L x n_obs)
+                lm["table"] = self._table(torch.cat([Z, x_obs], 0), spec, center, inv_ls)
+        return lm
+
+    def _basis(self, Z, n_basis, kernel, spec, center, inv_ls, lm):
+        """-> U (n x L), Uext (n x L')."""
+        o = self.opts
+        k_zo_w = lm["k_zo_w"]
+        # projector null spaces see the basis only through its row space: skip the final rotation (lowrank_basis)
+        rotate = o.rotate_basis if o.rotate_basis is not None else not (o.nullspace == "projector" and self.nullspace is None)
         if self.basis is not None:
             U = self.ops.f64(self.basis)
         elif spec is not None and o.gram == "cuda":
-            gram = self._gram_T(self._points(Z, spec, center, inv_ls), table_z)              # (L x L)
+            gram = self._gram_T(self._points(Z, spec, center, inv_ls), lm["table_z"])        # (L x L)
             if k_zo_w is not None:
-                gram = gram - k_zo_w @ k_oz
+                gram = gram - k_zo_w @ lm["k_oz"]
             gram = 0.5 * (gram + gram.T)
             gram = _psd.repair(gram, o.gate, assume_asymmetric=True)
-            U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr)
+            U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr, rotate=rotate)
         else:
             gram = kernel(Z, Z)
             gram = _psd.repair(gram, o.gate)
-            U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr)
-        if k_zo_w is not None:
-            uext_tail = -(U @ k_zo_w)
-        Uext = U if uext_tail is None else torch.cat([U, uext_tail], 1)
-        return U, Uext.contiguous(), table
+            U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr, rotate=rotate)
+        Uext = U if k_zo_w is None else torch.cat([U, -(U @ k_zo_w)], 1)
+        return U, Uext.contiguous()
+
+    def _nystrom(self, Z, n_basis, kernel, spec, center, inv_ls):
+        """-> U (n x L), Uext (n x L'), landmark table."""
+        lm = self._landmarks(Z, spec, center, inv_ls)
+        U, Uext = self._basis(Z, n_basis, kernel, spec, center, inv_ls, lm)
+        return U, Uext, lm["table"]
 
     # -----------------------------------------------------------------------------------------------------
     # one K1 pass over the local alive-list (fused kernel or generic callable)
@@ -284,14 +296,12 @@ class Recombiner:
         records = self._use_records(spec, d) and not self._bits
 
         clock.lap("setup")
-        U, Uext, table = self._nystrom(Z, num_pts - 1, kernel, spec, center, inv_ls)
-        clock.lap("nystrom")
-        n = U.shape[0]
+        lm = self._landmarks(Z, spec, center, inv_ls)
+        n = min(num_pts - 1, Z.shape[0]) if self.basis is None else self.basis.shape[0]
         S = 2 * (n + 1)
-        st = {"spec": spec, "table": table, "kernel": kernel, "X": X, "Z": Z,
+        st = {"spec": spec, "table": lm["table"], "kernel": kernel, "X": X, "Z": Z,
               "pts": (cand_bits if cand_bits is not None else self._points(X, spec, center, inv_ls))
               if (spec is not None and not records) else None}
-        UextT = Uext.T.contiguous()
 
         idx, mass, n_local = ops.compact_nonzero(mu)
         # every weight non-zero (the usual case): the alive-list is the identity and the record pass reads X as one
@@ -303,16 +313,10 @@ class Recombiner:
         obj = None if calc_obj is None else (-1 * calc_obj(pts_rec.to(dev))).to(torch.float64)
         clock.lap("compact+records")
 
-        while True:
-            if remaining <= S:
-                sel_idx, sel_w = self._finish(st, alive, n_local, pos0, remaining, n, UextT, row0, obj)
-                clock.lap("finish")
-                break
-            E = remaining // S
-            ES = E * S
-            idx, mass = alive.idx, alive.mass
+        def k1_pass(alive, n_local, pos0, remaining):
+            """Grouped kernel-column sums of one iteration: At, totw and the second count of the remainder."""
+            ES = (remaining // S) * S
             at, totw = self._accumulate(st, alive, n_local, pos0, ES, S)
-            clock.lap("k1")
             Lp = at.shape[1]
             t0 = min(max(ES - pos0, 0), n_local)           # first local offset belonging to the remainder
             extra = torch.zeros(Lp + 3, dtype=torch.float64, device=dev)
@@ -321,6 +325,41 @@ class Recombiner:
                 tail_at, tail_tw = self._accumulate(st, alive.tail(t0), n_local - t0, 0, n_local - t0, 1)
                 extra[:Lp] = tail_at[0]
                 extra[Lp] = tail_tw[0]
+            return at, totw, extra, t0
+
+        # The first (and by far the longest) K1 pass does not depend on the Nystrom basis: it runs on a stream confined
+        # to all SMs but a few (a green context) beside the range finder -- a host-driven sequence of ~300 small
+        # kernels (Cholesky-QR passes, eigh, refinement sweeps) that leaves most of the GPU idle.
+        first = {}
+        fork = contextlib.nullcontext()
+        if (remaining > S and o.overlap and o.stats is None and self.trace is None and dev.type == "cuda"
+                and self.basis is None and hasattr(ops, "partition_stream")):
+            part = ops.partition_stream()
+            if part is not None:
+                def launch_first():
+                    first["k1"] = k1_pass(alive, n_local, pos0, remaining)
+                    return first["k1"][:3]
+                fork = _nystrom.SideStream(launch_first, dev, part)
+        with fork:
+            U, Uext = self._basis(Z, n, kernel, spec, center, inv_ls, lm)
+        if U.shape[0] != n:                     # fewer landmarks than basis functions: the basis decides
+            n = U.shape[0]
+            S = 2 * (n + 1)
+            first.clear()
+        clock.lap("nystrom")
+        UextT = Uext.T.contiguous()
+
+        while True:
+            if remaining <= S:
+                sel_idx, sel_w = self._finish(st, alive, n_local, pos0, remaining, n, UextT, row0, obj)
+                clock.lap("finish")
+                break
+            E = remaining // S
+            ES = E * S
+            idx, mass = alive.idx, alive.mass
+            at, totw, extra, t0 = first.pop("k1") if "k1" in first else k1_pass(alive, n_local, pos0, remaining)
+            clock.lap("k1")
+            Lp = at.shape[1]
             objs = None
             if obj is not None:
                 objs = torch.zeros((S, 1), dtype=torch.float64, device=dev)

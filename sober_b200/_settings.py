@@ -15,7 +15,9 @@ L x L / S x S steps imitate the reference:
                    jitter -- and the null space taken as the trailing columns of the orthogonal projector
                    I - Q1 Q1^T (``nullspace="projector"``; ``"qr"`` = trailing columns of the complete Householder Q is
                    also available).  Same algorithm, different (equally valid) null-space basis: weights/moments
-                   invariants hold, indices are those of the oracle run with the same basis.
+                   invariants hold, indices are those of the oracle run with the same basis.  The projector depends on
+                   the Nystrom basis U only through its row space, so the range-finder basis Q^T is used as it is,
+                   without the q x q rotation by the singular vectors of Q^T K (``rotate_basis``).
 
 Every knob can be set individually; ``SOBER_B200_MODE`` picks the preset at import.
 """
@@ -35,6 +37,9 @@ class Options:
         self.generic_chunk = 1 << 16  # candidates per Gram tile on the generic path
         self.k1_variant = 0           # 0 auto (record / bit-packed kernels when they apply), 1 force the tiled kernel
         self.fused_projection = False  # hand-written DMMA projection+barycentre kernel instead of cuBLAS DGEMM
+        self.overlap = os.environ.get("SOBER_B200_OVERLAP", "1") != "0"   # first K1 pass beside the tail of the range finder (two streams); fast mode only
+        self.rotate_basis = None      # None: rotate the Nystrom basis by its singular vectors unless the null spaces come
+                                      # from the projector (then only span(U) matters); True / False force it
         self.stats = None             # optional dict that receives per-stage timings (forces syncs)
 
     def set_mode(self, mode):

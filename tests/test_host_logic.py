@@ -88,6 +88,19 @@ def test_fast_mode_equals_oracle_with_projector_nullspace(name):
     assert float((w - w_o).abs().max()) < 1e-8
 
 
+@pytest.mark.parametrize("name", ["matern6d_rest", "rbf_ard5d", "predcov_matern6d"])
+def test_projector_mode_sees_only_the_span_of_the_basis(name):
+    """With projector null spaces the result is a function of span(U): the un-rotated range-finder basis Q^T (what fast
+    mode uses) and the singular-vector basis of torch.svd_lowrank select the same points with the same weights."""
+    case = Case(name)
+    out = {}
+    for rotate in (True, False):
+        torch.manual_seed(11)
+        out[rotate] = run_host(case, "fast", rotate_basis=rotate)
+    assert torch.equal(out[True][0], out[False][0])
+    assert float((out[True][1] - out[False][1]).abs().max()) < 1e-9
+
+
 def test_feature_means_preserved_without_remainder():
     """N = S * 2^k: sum_i w_i phi(x_i) == sum_i mu_i phi(x_i) for the Nystrom features (SURVEY.md TL;DR 4)."""
     case = Case("matern6d_pow2")
