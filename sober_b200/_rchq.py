@@ -394,9 +394,16 @@ class Recombiner:
                 bary = bary / totw.unsqueeze(1)
                 design = None
             clock.lap("tail+project")
-            wfull = _car.caratheodory(ops, bary, totw, o.nullspace, self.nullspace, design=design)
-            kept = wfull > 0
-            flags = torch.cat([kept, torch.isfinite(wfull).all().reshape(1)]).tolist()   # the one host sync of the iteration
+            rank = None
+            if (design is None and self.nullspace is None and o.nullspace == "projector" and objs is None
+                    and self.trace is None):
+                # the whole step (null space, elimination, survivor flags and ranks) as one CUDA-graph replay
+                wfull, kept, flagvec, rank = _car.reduce_step(ops, bary, totw, use_graph=o.graphs and o.stats is None)
+                flags = flagvec.tolist()                                                 # the one host sync of the iteration
+            else:
+                wfull = _car.caratheodory(ops, bary, totw, o.nullspace, self.nullspace, design=design)
+                kept = wfull > 0
+                flags = torch.cat([kept, torch.isfinite(wfull).all().reshape(1)]).tolist()   # the one host sync
             n_design = (design.shape[1] if design is not None else bary.shape[1] + 1)
             if self.nullspace is None and _car.needs_retry(o.nullspace, sum(flags[:-1]), n_design, flags[-1]):
                 if o.stats is not None:
@@ -404,12 +411,15 @@ class Recombiner:
                 wfull = _car.caratheodory(ops, bary, totw, "qr", design=design)
                 kept = wfull > 0
                 flags = kept.tolist() + [True]
+                rank = None
             clock.lap("car")
             if obj is not None:
                 wfull = self._objective_step(bary[:, :n], bary[:, n], wfull)
                 kept = wfull > 0
                 flags = kept.tolist() + [True]
-            rank = (torch.cumsum(kept.to(torch.int32), 0) - kept.to(torch.int32)).to(torch.int32)
+                rank = None
+            if rank is None:
+                rank = (torch.cumsum(kept.to(torch.int32), 0) - kept.to(torch.int32)).to(torch.int32)
             keep = KeepMap(flags[:-1], S, ES)
             new_pos0 = keep.before(pos0)
             new_local = keep.before(pos0 + n_local) - new_pos0

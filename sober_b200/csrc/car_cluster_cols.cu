@@ -390,7 +390,16 @@ extern "C" int sober_car_cluster_cols_profiled(double* basis, int32_t k, int32_t
     void (*kern)(const CarColsParams) = nullptr;
     if (rmax == 32) kern = exact ? car_cols_kernel<32, true> : car_cols_kernel<32, false>;
     else kern = exact ? car_cols_kernel<56, true> : car_cols_kernel<56, false>;
-    SOBER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {   // the > 48 KB opt-in is per device and sticky: once per (device, kernel variant), never inside a graph capture
+        static int configured[64][4] = {};
+        int dev = 0;
+        SOBER_CUDA_CHECK(cudaGetDevice(&dev));
+        const int variant = (rmax == 32 ? 0 : 2) + (exact ? 1 : 0);
+        if (dev < 0 || dev >= 64 || configured[dev][variant] < (int)smem) {
+            SOBER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (dev >= 0 && dev < 64) configured[dev][variant] = (int)smem;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CE_P);
     cfg.blockDim = dim3(CE_THREADS);
