@@ -334,7 +334,11 @@ def main():
             "bound": "fp64",          # FP64 FMA pipe; the hbm|tensor enum has no entry for it
             "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": (k1_tflops / fp64_peak) if k1_tflops else None,
-            "traffic": None,
+            # DRAM bytes of the largest launch (10^6 candidates x 1000 landmarks) from the ncu --set full capture
+            # profiles/r01_ncu_final_k1_and_car_cols.txt: 64.1 MB read + 7.6 MB written; the 64-byte records alone are
+            # 64 MB, i.e. no re-reads.  Only quoted for the shape it was captured on.
+            "traffic": (71.7e6 if (name == "c2" and world == 1 and not args.pred_cov) else None),
+            "traffic_unit": "bytes per largest launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
             "peak_source": "measured in this run: dependent-chain DFMA probe (sober_fp64_probe), 2 flop per FMA",
             "algorithmic_flop_per_pair": flop_per_pair, "pairs_per_step": k1_pairs / max(args.steps, 1),
             "launches": k1_calls, "ms_per_step": k1_ms / max(args.steps, 1),

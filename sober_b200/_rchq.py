@@ -469,10 +469,14 @@ class Recombiner:
         if obj is not None:
             alive_obj = obj[all_idx]
             feats = torch.cat([feats, alive_obj.unsqueeze(1)], 1)
-        wfull = _car.caratheodory(ops, feats, all_mass, o.nullspace, self.nullspace)
         if self.nullspace is None and o.nullspace == "projector":
-            if _car.needs_retry("projector", int((wfull > 0).sum()), feats.shape[1] + 1, bool(torch.isfinite(wfull).all())):
+            wfull, _, flagvec, _ = _car.reduce_step(ops, feats, all_mass,
+                                                    use_graph=o.graphs and o.stats is None and self.trace is None)
+            flags = flagvec.tolist()
+            if _car.needs_retry("projector", sum(flags[:-1]), feats.shape[1] + 1, flags[-1]):
                 wfull = _car.caratheodory(ops, feats, all_mass, "qr")
+        else:
+            wfull = _car.caratheodory(ops, feats, all_mass, o.nullspace, self.nullspace)
         if obj is not None:
             # NB the reference indexes ``obj`` with POSITIONS here (SOBER/_rchq.py:89), kept as is
             live = torch.nonzero(wfull > 0).reshape(-1)
