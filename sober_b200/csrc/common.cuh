@@ -63,6 +63,15 @@ static __device__ const double EXP2_TAB[EXP_TAB_SIZE] = {  // 2^(j/64), correctl
     1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
     1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
 
+// 64-bit constants of the routines below.  Read as constant-bank operands (DFMA ..., c[0x3][..]) they cost no
+// instruction; as literals the compiler rebuilds each one with two UMOV/IMAD.MOV per use (measured in the K1 SASS:
+// 6 of 48 instructions per kernel value).
+static __constant__ double MATH_C[6] = {
+    -92.33248261689366,       // [0] -64 / ln2
+    0.010830424696249145,     // [1] ln2 / 64 rounded to double
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,   // [2..4] exp polynomial
+    1.0 / 3.0};               // [5] Matern-5/2
+
 __device__ __forceinline__ void load_exp_table(double* tab_smem, int tid, int nthreads) {
     for (int j = tid; j < EXP_TAB_SIZE; j += nthreads) tab_smem[j] = EXP2_TAB[j];
 }
@@ -78,8 +87,8 @@ __device__ __forceinline__ double lds_f64(uint32_t saddr) {
 __device__ __forceinline__ double exp_neg(double s_in, uint32_t tab) {
     // exp(-s) = 2^m * 2^(j/64) * exp(r),  -s = (64 m + j) ln2/64 + r,  |r| <= ln2/128
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: adds round-to-nearest-integer
-    const double NEG_L2E64 = -92.33248261689366;        // -64 / ln2
-    const double LN2_64 = 0.010830424696249145;         // ln2/64 rounded to double
+    const double NEG_L2E64 = MATH_C[0];                 // -64 / ln2
+    const double LN2_64 = MATH_C[1];                    // ln2/64 rounded to double
     // clamp s at ~700 through the integer pipe (s >= 0: high words order like ints): below 1e-304 the exponent
     // trick at the end would wrap
     const double s = __hiloint2double(min(__double2hiint(s_in), 0x4085E000), __double2loint(s_in));
@@ -89,8 +98,8 @@ __device__ __forceinline__ double exp_neg(double s_in, uint32_t tab) {
     // one FMA: the product kf * LN2_64 is exact inside the FMA, so r carries only the rounding of the constant
     // (|s| * 1.1e-16 absolute) -- no hi/lo split needed
     const double r = fma(kf, -LN2_64, -s);
-    double q = fma(1.0 / 120.0, r, 1.0 / 24.0);
-    q = fma(q, r, 1.0 / 6.0);
+    double q = fma(MATH_C[2], r, MATH_C[3]);
+    q = fma(q, r, MATH_C[4]);
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     const double p = fma(q, r, 1.0);
@@ -144,7 +153,7 @@ __device__ __forceinline__ double stationary_value(double d2, uint32_t tab) {
     const double ex = exp_neg(r, tab);
     if (FAM == SOBER_MATERN12) return ex;
     if (FAM == SOBER_MATERN32) return (1.0 + r) * ex;
-    return fma(a, 1.0 / 3.0, 1.0 + r) * ex;
+    return fma(a, MATH_C[5], 1.0 + r) * ex;
 }
 
 __device__ __forceinline__ double tanimoto_value(double dot, double xn, double zn) {

@@ -50,7 +50,7 @@ constexpr int REC_STAGES = 3;
 #ifndef SOBER_REC_MINB
 #define SOBER_REC_MINB 2
 #endif
-template <int D, int FAM, int TL, int TG>
+template <int D, int FAM, int TL, int TG, bool UNIT>
 __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_kernel(const GroupParams p) {
     constexpr int LDR = (D + 3) / 2 * 2;  // d + 2 rounded up to even
     __shared__ __align__(16) double buf[REC_STAGES][REC_ROWS][TG][LDR];
@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_ker
     const bool active = l0 < p.L;
 
     load_exp_table(tab, t, REC_THREADS);
-    const uint32_t tab_s = smem_addr(tab);
+    uint32_t tab_s = smem_addr(tab);
+    asm volatile("" : "+r"(tab_s));   // opaque: otherwise the address is re-derived (S2UR + ULEA + ...) at every use
     if (t == 0) {
         for (int s = 0; s < REC_STAGES; ++s) mbar_init(&bars[s], 1);
         mbar_fence_init();
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_ker
 #pragma unroll
                 for (int j = 0; j < TG; ++j)
                     if (j >= ja && j < jb && (e0 + r) * p.S + g0 + j < p.ES)
-                        tw[j] += p.unit_weights ? 1.0 : buf[stage][r][j][D + 1];
+                        tw[j] += UNIT ? 1.0 : buf[stage][r][j][D + 1];
             }
         }
         if (active) {
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_ker
 #pragma unroll
                         for (int k = 0; k < D; ++k) x[j][k] = rp[k];
                         xn[j] = rp[D];
-                        w[j] = p.unit_weights ? 1.0 : rp[D + 1];
+                        w[j] = UNIT ? 1.0 : rp[D + 1];
                     }
                     double val[TL][TG];
 #pragma unroll
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_ker
                         if (j < ja || j >= jb) continue;
                         const double* rp = &buf[stage][r][j][0];
                         const double xn = rp[D];
-                        const double w = p.unit_weights ? 1.0 : rp[D + 1];
+                        const double w = UNIT ? 1.0 : rp[D + 1];
 #pragma unroll
                         for (int i = 0; i < TL; ++i) {
                             double dot = (FAM == SOBER_TANIMOTO) ? 0.0 : zn[i];
@@ -571,7 +572,10 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
 
 template <int D, int FAM>
 static void launch_records(const Plan& pl, const GroupParams& p, cudaStream_t st) {
-    group_records_kernel<D, FAM, REC_TL, REC_TG><<<pl.grid, pl.block, 0, st>>>(p);
+    if (p.unit_weights)
+        group_records_kernel<D, FAM, REC_TL, REC_TG, true><<<pl.grid, pl.block, 0, st>>>(p);
+    else
+        group_records_kernel<D, FAM, REC_TL, REC_TG, false><<<pl.grid, pl.block, 0, st>>>(p);
 }
 
 template <int FAM>
