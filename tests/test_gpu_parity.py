@@ -4,6 +4,7 @@ and the reference-generated golden fixtures.
 Tolerances (BASELINE.json north_star): kernel / feature matrices 1e-10 relative in f64; weights 1e-6 (asserted
 much tighter); indices identical; integer/index work bit-exact.
 """
+import ctypes as C
 import os
 import warnings
 
@@ -666,3 +667,73 @@ def test_full_size_invariants(ops, cuda_device, n_cand):
         assert err < 1e-11
     else:
         assert err < 0.2
+
+
+# ------------------------------------------------------------------------------------------------------------
+# streams and graphs: scheduling only, results must not move
+# ------------------------------------------------------------------------------------------------------------
+def test_partition_stream_runs_kernels(ops, cuda_device):
+    """sober_partition_stream: a stream confined to fewer SMs than the device has; kernels launched on it run and
+    order with the main stream through events."""
+    from sober_b200._linalg import cholesky_upper
+    part = ops.partition_stream()
+    if part is None:
+        pytest.skip("driver cannot partition the device (no green contexts)")
+    sms = C.c_int()
+    from sober_b200 import _lib
+    _lib.check(_lib.load().sober_sm_count(C.byref(sms)), "sm_count")
+    assert 0 < ops.partition_sms < sms.value
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(300, 120, dtype=torch.float64, generator=g).to(cuda_device)
+    gram = a.T @ a
+    part.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(part):
+        r, info = cholesky_upper(gram)
+        r.record_stream(torch.cuda.current_stream())
+    torch.cuda.current_stream().wait_stream(part)
+    assert int(info) == 0 and rel(r.T @ r, gram) < 1e-13
+
+
+@pytest.mark.parametrize("name", ["matern6d_rest", "predcov_matern6d", "tanimoto256"])
+def test_overlap_and_graphs_do_not_change_results(ops, cuda_device, name):
+    """The SM-partitioned first K1 pass and the CUDA-graph replay of the Caratheodory steps are pure scheduling: the
+    same indices and weights as the plain single-stream, eager run (three calls each, so that graphs get captured
+    and replayed)."""
+    import sober_b200
+    case = Case(name, cuda_device)
+    kern = case.kernel()
+
+    def run(**kw):
+        outs = []
+        with warnings.catch_warnings(), sober_b200.configure(mode="fast", **kw):
+            warnings.simplefilter("ignore")
+            for _ in range(3):
+                torch.manual_seed(21)
+                mu = None if case.mu is None else case.mu.clone()
+                outs.append(sober_b200.recombination(case.X, case.Z, case.b, kern, None, None, init_weights=mu))
+        return outs
+
+    plain = run(overlap=False, graphs=False)
+    fancy = run(overlap=True, graphs=True)
+    # (cuBLAS may pick another GEMM algorithm under capture: weights to rounding, indices exactly)
+    for (i0, w0), (i1, w1) in zip(plain, fancy):
+        assert torch.equal(i0, i1) and float((w0 - w1).abs().max()) < 1e-12
+    assert torch.equal(plain[0][0], plain[2][0]) and torch.equal(plain[0][1], plain[2][1])
+
+
+def test_full_size_overlap_and_graphs(ops, cuda_device):
+    """Same at BASELINE configs[1] size (N = 1e6, where the first K1 pass really runs beside the range finder)."""
+    import sober_b200
+    g = torch.Generator(device=cuda_device).manual_seed(0)
+    n_cand = 1_000_000
+    X = torch.rand(n_cand, 6, dtype=torch.float64, device=cuda_device, generator=g)
+    Z = X[torch.randperm(n_cand, device=cuda_device, generator=g)[:1000]].clone()
+    kern = ok.Kernel(ok.BareModel(ok.make_kernel("matern", [0.5], 1.0).to(cuda_device)), mode="kernel")
+    res = {}
+    for fancy in (False, True):
+        with warnings.catch_warnings(), sober_b200.configure(mode="fast", overlap=fancy, graphs=fancy):
+            warnings.simplefilter("ignore")
+            for _ in range(2):
+                torch.manual_seed(5)
+                res[fancy] = sober_b200.recombination(X, Z, 200, kern, None, None)
+    assert torch.equal(res[False][0], res[True][0]) and float((res[False][1] - res[True][1]).abs().max()) < 1e-12
