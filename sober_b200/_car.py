@@ -114,13 +114,16 @@ _graphs = {}
 
 
 def _reduce_step(ops, feats, mass):
-    """feats (S x n), mass (S,) -> weights (S,), kept mask, [kept..., all-finite] flags, exclusive rank of the kept."""
+    """feats (S x n), mass (S,) -> weights (S,), kept mask, host summary, exclusive rank of the kept.
+    The host summary is int32 [inclusive cumulative count of kept groups (S) | all weights finite (1)]: one small
+    device-to-host copy gives the host everything it needs (``KeepMap.from_summary``)."""
     wfull = caratheodory(ops, feats, mass, "projector")
     kept = wfull > 0
-    flags = torch.cat([kept, torch.isfinite(wfull).all().reshape(1)])
     k32 = kept.to(torch.int32)
-    rank = (torch.cumsum(k32, 0) - k32).to(torch.int32)
-    return wfull, kept, flags, rank
+    cum = torch.cumsum(k32, 0).to(torch.int32)
+    rank = cum - k32
+    summary = torch.cat([cum, torch.isfinite(wfull).all().reshape(1).to(torch.int32)])
+    return wfull, kept, summary, rank
 
 
 class _ReduceGraph:

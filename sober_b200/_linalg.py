@@ -7,13 +7,25 @@ q <= 224 it is the register-resident 2-CTA cluster kernel of ``csrc/chol_pair.cu
 ``solve_right_upper(r, y)`` solves ``X @ r = y`` for upper-triangular ``r``.  On a CUDA tensor with q <= 256 it calls
 the hand-written warp-per-row kernel (``csrc/small_linalg.cu``); otherwise (CPU tensors in the host-logic tests,
 larger q) it is ``torch.linalg.solve_triangular``."""
+import contextlib
 import ctypes as C
 
 import torch
 
 from . import _lib
 
+_NO_GUARD = contextlib.nullcontext()
+
 launches = 0   # kernels launched from this module (bench.py adds them to its gpu_launches claim)
+
+
+def _raw_stream(device):
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    return index, C.c_void_p(torch._C._cuda_getCurrentRawStream(index))
+
+
+def _guard(device, index):
+    return _NO_GUARD if torch._C._cuda_getDevice() == index else torch.cuda.device(device)
 
 
 def cholesky_upper(g):
@@ -23,11 +35,11 @@ def cholesky_upper(g):
         g = g.contiguous()
         r = torch.empty_like(g)
         info = torch.empty((), dtype=torch.int32, device=g.device)
-        with torch.cuda.device(g.device):
+        index, stream = _raw_stream(g.device)
+        with _guard(g.device, index):
             _lib.check(lib.sober_cholesky_upper(
                 C.c_void_p(g.data_ptr()), g.stride(0), q, C.c_void_p(r.data_ptr()), r.stride(0),
-                C.c_void_p(info.data_ptr()), C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)),
-                "cholesky_upper")
+                C.c_void_p(info.data_ptr()), stream), "cholesky_upper")
         global launches
         launches += 1
         return r, info
@@ -44,11 +56,11 @@ def solve_right_upper(r, y):
             r = r.clone()              # the kernel fetches R with TMA bulk copies (16-byte aligned base)
         y = y.contiguous()
         out = torch.empty_like(y)
-        with torch.cuda.device(y.device):
+        index, stream = _raw_stream(y.device)
+        with _guard(y.device, index):
             _lib.check(lib.sober_trsm_right_upper(
                 C.c_void_p(y.data_ptr()), y.stride(0), C.c_void_p(r.data_ptr()), r.stride(0), y.shape[0], q,
-                C.c_void_p(out.data_ptr()), out.stride(0), C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)),
-                "trsm_right_upper")
+                C.c_void_p(out.data_ptr()), out.stride(0), stream), "trsm_right_upper")
         global launches
         launches += 1
         return out

@@ -4,6 +4,7 @@
 otherwise (no CPU fallback).  Tensors are allocated by torch (caching allocator), kernels are enqueued on
 torch's current stream; nothing here synchronises except where a count has to reach the host.
 """
+import contextlib
 import ctypes as C
 import os
 
@@ -46,6 +47,9 @@ class LandmarkTable:
         self.d = zt.shape[1] if d is None else int(d)
 
 
+_NO_GUARD = contextlib.nullcontext()
+
+
 class CudaOps:
     def __init__(self, device=None):
         if not torch.cuda.is_available():
@@ -54,18 +58,34 @@ class CudaOps:
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.variant = 0
-        self._ws = None
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._ws = {}
         self.launches = 0      # kernels launched through the C ABI (bench.py reports it)
         self.timing = None     # None, or {name: [(start_event, end_event, work), ...]} filled per call
 
     # -- helpers -------------------------------------------------------------------------------------
+    # The wrappers below run a dozen times per loop iteration between a host sync and the next big kernel, i.e. with the
+    # GPU idle: torch.cuda.current_stream() (8 us: builds a Stream object) and the torch.cuda.device() guard (7 us)
+    # are replaced by their raw equivalents.
+    def _stream_ptr(self):
+        return torch._C._cuda_getCurrentRawStream(self.index)
+
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(self.index))
+
+    def _guard(self):
+        """Device guard that costs nothing when the current device already is ours (one process per GPU)."""
+        if torch._C._cuda_getDevice() == self.index:
+            return _NO_GUARD
+        return torch.cuda.device(self.device)
 
     def _workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=self.device)
-        return self._ws
+        # one workspace per stream: the first K1 pass runs on the SM-partitioned stream beside work on the main one
+        key = self._stream_ptr()
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = self._ws[key] = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=self.device)
+        return ws
 
     def f64(self, t):
         return t.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
@@ -105,7 +125,7 @@ class CudaOps:
         n, d = X.shape
         ldp = (d + 1 + 1) // 2 * 2  # even row stride keeps rows 16-byte aligned
         P = torch.empty((n, ldp), dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("prepare_points")
             check(self.lib.sober_prepare_points(_ptr(X), X.stride(0), n, d, _ptr(center), _ptr(inv_ls), _ptr(P), ldp,
                                                 self._stream()), "prepare_points")
@@ -119,7 +139,7 @@ class CudaOps:
         m = X.shape[0] if idx is None else idx.numel()
         ldr = record_stride(d)
         rec = torch.empty((m, ldr), dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("make_records")
             check(self.lib.sober_make_records(_ptr(X), X.stride(0), d, _ptr(center), _ptr(inv_ls), _ptr(idx), _ptr(mu),
                                               m, _ptr(rec), ldr, self._stream()), "make_records")
@@ -137,7 +157,7 @@ class CudaOps:
         words = torch.empty((n, W), dtype=torch.int64, device=self.device)
         popc = torch.empty(n, dtype=torch.float64, device=self.device)
         flag = torch.zeros(1, dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("pack_bits")
             check(self.lib.sober_pack_bits(_ptr(X), X.stride(0), n, d, _ptr(words), W, _ptr(popc), _ptr(flag),
                                            self._stream()), "pack_bits")
@@ -149,7 +169,7 @@ class CudaOps:
         """Tanimoto layout: the rows as they are plus |x|^2."""
         n, d = X.shape
         xn = torch.empty(n, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             check(self.lib.sober_row_sqnorm(_ptr(X), X.stride(0), n, d, _ptr(xn), self._stream()), "row_sqnorm")
         self.launches += 1
         return PointSet(X, X.stride(0), xn, 1, n, d)
@@ -162,7 +182,7 @@ class CudaOps:
         cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
         nbytes = self.lib.sober_compact_workspace(n)
         ws = self._workspace(nbytes)
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("compact_nonzero")
             check(self.lib.sober_compact_nonzero(_ptr(mu), n, _ptr(idx), _ptr(out), _ptr(cnt), _ptr(ws), ws.numel(),
                                                  self._stream()), "compact_nonzero")
@@ -198,7 +218,7 @@ class CudaOps:
         if nbytes < 0:
             raise _lib.SoberB200Error("sober_b200: group_accumulate: bad arguments")
         ws = self._workspace(nbytes)
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("group_accumulate")
             check(self.lib.sober_group_accumulate(C.byref(a), _ptr(ws), ws.numel(), self._stream()),
                   "group_accumulate")
@@ -208,7 +228,7 @@ class CudaOps:
 
     def group_accumulate_gram(self, G, mu, pos_begin, ES, S, At, totw):
         L, m = G.shape
-        with torch.cuda.device(self.device):
+        with self._guard():
             check(self.lib.sober_group_accumulate_gram(_ptr(G), G.stride(0), L, m, _ptr(mu), int(pos_begin), int(ES),
                                                        int(S), _ptr(At), _ptr(totw), self._stream()),
                   "group_accumulate_gram")
@@ -223,7 +243,7 @@ class CudaOps:
         steps = torch.zeros(1, dtype=torch.int32, device=self.device) if want_pivots else None
         nbytes = self.lib.sober_car_workspace(k)
         flags = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("car_eliminate")
             check(self.lib.sober_car_eliminate(_ptr(basis_rows), k, S, _ptr(mass), int(bool(exact)), _ptr(piv), _ptr(steps),
                                                _ptr(flags),
@@ -239,7 +259,7 @@ class CudaOps:
         n = uext.shape[0]
         design = torch.empty((S, n + 1), dtype=torch.float64, device=self.device)
         totw_out = torch.empty(S, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("project_design")
             check(self.lib.sober_project_design(_ptr(at), at.stride(0), _ptr(tail), _ptr(totw), _ptr(tail_tw), _ptr(uext),
                                                 uext.stride(0), S, Lp, n, _ptr(design), design.stride(0), _ptr(totw_out),
@@ -250,7 +270,7 @@ class CudaOps:
 
     def car_cluster_fits(self, S, n_prime, have_basis):
         """Cluster size the fused CAR kernel would use for this shape, 0 if it does not fit in distributed smem."""
-        with torch.cuda.device(self.device):
+        with self._guard():
             return int(self.lib.sober_car_cluster_fits(int(S), int(n_prime), int(bool(have_basis))))
 
     def car_cluster(self, mass, design=None, basis_rows=None, exact=False):
@@ -263,7 +283,7 @@ class CudaOps:
         else:
             S = basis_rows.shape[1]
             n_prime = S - basis_rows.shape[0]
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("car_cluster")
             check(self.lib.sober_car_cluster(_ptr(design) if basis_rows is None else None, _ptr(basis_rows), int(S),
                                              int(n_prime), _ptr(mass), int(bool(exact)), None, self._stream()),
@@ -272,14 +292,14 @@ class CudaOps:
         self.launches += 1
 
     def car_cols_fits(self, S, k):
-        with torch.cuda.device(self.device):
+        with self._guard():
             return int(self.lib.sober_car_cluster_cols_fits(int(S), int(k)))
 
     def car_cols(self, basis_rows, mass, exact=False):
         """Elimination on ``basis_rows`` (k x S) with the column-distributed cluster kernel; ``mass`` reduced in place."""
         k, S = basis_rows.shape
         assert basis_rows.is_contiguous() and mass.is_contiguous()
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("car_cols")
             check(self.lib.sober_car_cluster_cols(_ptr(basis_rows), k, S, _ptr(mass), int(bool(exact)), None,
                                                   self._stream()), "car_cluster_cols")
@@ -293,7 +313,7 @@ class CudaOps:
         mu_out = torch.empty(n_out, dtype=torch.float64, device=self.device)
         ldr = 0 if rec is None else rec.stride(0)
         rec_out = None if rec is None else torch.empty((n_out, ldr), dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             t0 = self._begin("update_compact")
             check(self.lib.sober_update_compact(_ptr(idx), _ptr(mu), int(n_local), int(pos0), int(ES), int(S),
                                                 _ptr(wstar), _ptr(totw), _ptr(rank), int(K), int(bool(tail_keep)),
@@ -305,7 +325,7 @@ class CudaOps:
         return idx_out, mu_out, rec_out
 
     def scatter_result(self, dst, idx, w):
-        with torch.cuda.device(self.device):
+        with self._guard():
             check(self.lib.sober_scatter_result(_ptr(dst), dst.numel(), _ptr(idx), _ptr(w), idx.numel(),
                                                 self._stream()), "scatter_result")
         self.launches += 1
@@ -318,7 +338,7 @@ class CudaOps:
             self._partition = None
             if reserve > 0:
                 ptr, sms = C.c_void_p(), C.c_int32()
-                with torch.cuda.device(self.device):
+                with self._guard():
                     _lib.check(self.lib.sober_partition_stream(reserve, C.byref(ptr), C.byref(sms)), "partition_stream")
                 if ptr.value:
                     self._partition = torch.cuda.ExternalStream(ptr.value, device=self.device)
@@ -327,5 +347,5 @@ class CudaOps:
 
     def fp64_probe(self, blocks, iters):
         sink = torch.zeros(1, dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
+        with self._guard():
             check(self.lib.sober_fp64_probe(int(blocks), int(iters), _ptr(sink), self._stream()), "fp64_probe")

@@ -75,6 +75,17 @@ class KeepMap:
         self.K = self.cum[S]
         self.tail_keep = bool(kept_mask[S - 1])
 
+    @classmethod
+    def from_summary(cls, summary, S, ES):
+        """From the inclusive cumulative kept-count the device computed (``_car._reduce_step``): no Python loop over
+        the groups (this runs between the host sync and the next kernel launch, with the GPU idle)."""
+        self = cls.__new__(cls)
+        self.S, self.ES, self.E = S, ES, ES // S
+        self.cum = [0] + summary[:S]
+        self.K = self.cum[S]
+        self.tail_keep = self.cum[S] > self.cum[S - 1]
+        return self
+
     def before(self, p):
         """Number of surviving positions strictly below global position p."""
         if p <= self.ES:
@@ -394,33 +405,37 @@ class Recombiner:
                 bary = bary / totw.unsqueeze(1)
                 design = None
             clock.lap("tail+project")
-            rank = None
+            rank = keep = None
+            n_design = (design.shape[1] if design is not None else bary.shape[1] + 1)
             if (design is None and self.nullspace is None and o.nullspace == "projector" and objs is None
                     and self.trace is None):
-                # the whole step (null space, elimination, survivor flags and ranks) as one CUDA-graph replay
-                wfull, kept, flagvec, rank = _car.reduce_step(ops, bary, totw, use_graph=o.graphs and o.stats is None)
-                flags = flagvec.tolist()                                                 # the one host sync of the iteration
+                # the whole step (null space, elimination, survivor counts and ranks) as one CUDA-graph replay
+                wfull, kept, summary, rank = _car.reduce_step(ops, bary, totw, use_graph=o.graphs and o.stats is None)
+                summary = summary.tolist()                                               # the one host sync of the iteration
+                keep = KeepMap.from_summary(summary, S, ES)
+                retry = _car.needs_retry("projector", keep.K, n_design, bool(summary[S]))
             else:
                 wfull = _car.caratheodory(ops, bary, totw, o.nullspace, self.nullspace, design=design)
                 kept = wfull > 0
                 flags = torch.cat([kept, torch.isfinite(wfull).all().reshape(1)]).tolist()   # the one host sync
-            n_design = (design.shape[1] if design is not None else bary.shape[1] + 1)
-            if self.nullspace is None and _car.needs_retry(o.nullspace, sum(flags[:-1]), n_design, flags[-1]):
+                retry = self.nullspace is None and _car.needs_retry(o.nullspace, sum(flags[:-1]), n_design, flags[-1])
+            if retry:
                 if o.stats is not None:
                     o.stats["car_retries"] = o.stats.get("car_retries", 0) + 1
                 wfull = _car.caratheodory(ops, bary, totw, "qr", design=design)
                 kept = wfull > 0
                 flags = kept.tolist() + [True]
-                rank = None
+                rank = keep = None
             clock.lap("car")
             if obj is not None:
                 wfull = self._objective_step(bary[:, :n], bary[:, n], wfull)
                 kept = wfull > 0
                 flags = kept.tolist() + [True]
-                rank = None
+                rank = keep = None
             if rank is None:
                 rank = (torch.cumsum(kept.to(torch.int32), 0) - kept.to(torch.int32)).to(torch.int32)
-            keep = KeepMap(flags[:-1], S, ES)
+            if keep is None:
+                keep = KeepMap(flags[:-1], S, ES)
             new_pos0 = keep.before(pos0)
             new_local = keep.before(pos0 + n_local) - new_pos0
             alive = Alive(*ops.update_compact(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, keep.K,
@@ -470,10 +485,10 @@ class Recombiner:
             alive_obj = obj[all_idx]
             feats = torch.cat([feats, alive_obj.unsqueeze(1)], 1)
         if self.nullspace is None and o.nullspace == "projector":
-            wfull, _, flagvec, _ = _car.reduce_step(ops, feats, all_mass,
+            wfull, _, summary, _ = _car.reduce_step(ops, feats, all_mass,
                                                     use_graph=o.graphs and o.stats is None and self.trace is None)
-            flags = flagvec.tolist()
-            if _car.needs_retry("projector", sum(flags[:-1]), feats.shape[1] + 1, flags[-1]):
+            summary = summary.tolist()
+            if _car.needs_retry("projector", summary[-2], feats.shape[1] + 1, bool(summary[-1])):
                 wfull = _car.caratheodory(ops, feats, all_mass, "qr")
         else:
             wfull = _car.caratheodory(ops, feats, all_mass, o.nullspace, self.nullspace)
