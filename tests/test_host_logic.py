@@ -121,6 +121,22 @@ def test_feature_means_preserved_without_remainder():
     assert float((full - sel).abs().max()) < 1e-12
 
 
+def test_keepmap_from_device_summary_equals_mask_constructor():
+    """KeepMap.from_summary (inclusive cumulative kept-count, as _car._reduce_step returns it) == KeepMap(mask)."""
+    g = torch.Generator().manual_seed(1)
+    for S, R in [(6, 47), (10, 1003), (400, 1_000_000), (4, 9)]:
+        ES = (R // S) * S
+        for last in (True, False):
+            kept = (torch.rand(S, generator=g) < 0.5)
+            kept[S - 1] = last
+            summary = torch.cat([torch.cumsum(kept.to(torch.int32), 0).to(torch.int32),
+                                 torch.ones(1, dtype=torch.int32)]).tolist()
+            a, b = KeepMap(kept.tolist(), S, ES), KeepMap.from_summary(summary, S, ES)
+            assert (a.K, a.tail_keep, a.cum) == (b.K, b.tail_keep, b.cum)
+            for p in (0, 1, S - 1, S, ES - 1, ES, ES + 1, R):
+                assert a.before(p) == b.before(p)
+
+
 def test_keepmap_counts_match_mask_bookkeeping():
     g = torch.Generator().manual_seed(0)
     for S, R in [(6, 47), (6, 48), (10, 1003), (4, 9)]:
