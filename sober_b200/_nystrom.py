@@ -81,7 +81,7 @@ def _orthonormal_basis(y, how, check=True, passes=2):
     return torch.linalg.qr(y).Q
 
 
-def lowrank_basis(gram, rank, niter=2, qr="householder", rotate=True):
+def lowrank_basis(gram, rank, niter=2, qr="householder", rotate=True, probe=None):
     """-(Q @ svd(Q^T K).U)^T of torch.svd_lowrank, with the same single random draw.
 
     ``qr="householder"`` and no injected test matrix: ``torch.svd_lowrank`` itself (parity mode).  Otherwise the same
@@ -94,11 +94,12 @@ def lowrank_basis(gram, rank, niter=2, qr="householder", rotate=True):
     that the recombination sees when its null spaces come from the orthogonal projector (``_car.projector_rows`` is a
     function of range([1 | features]) alone; the terminal branches and the objective step likewise).  The rotation is
     the most expensive N-independent item of the call (eigh + refinement: 2.7 ms of 20 at BASELINE configs[1])."""
-    if _injected_test_matrix is None and qr == "householder":
+    if _injected_test_matrix is None and qr == "householder" and probe is None:
         left, _, _ = torch.svd_lowrank(gram, q=rank, niter=niter)
         return -1 * left.T
     size = gram.shape[-1]
-    probe = draw_test_matrix(size, rank, gram.dtype, gram.device)
+    if probe is None:                                     # (a caller that may need to redo the call draws it itself)
+        probe = draw_test_matrix(size, rank, gram.dtype, gram.device)
     # range(Q) after the last orthonormalisation is range(K (K^T K)^niter Omega) whatever the intermediate bases
     # were: those only keep the columns from collapsing onto the dominant eigenvector, for which one Cholesky-QR
     # pass (orthonormal to eps cond^2) does as well as two.  The last basis is orthonormalised to rounding.

@@ -38,6 +38,11 @@ def repair(cov, gate, assume_asymmetric=False, max_iter=10):
     cov = torch.sqrt(cov * cov.T)
     if passes(cov, gate):
         return cov
+    return escalate(cov, gate, max_iter)
+
+
+def escalate(cov, gate, max_iter=10):
+    """The jitter loop of the repair (SOBER/_utils.py:145-157), for a matrix that has just failed the test."""
     size = cov.size(0)
     bump = torch.full((size,), 1e-5, dtype=cov.dtype, device=cov.device)
     rounds = 0
@@ -49,3 +54,43 @@ def repair(cov, gate, assume_asymmetric=False, max_iter=10):
         if rounds > max_iter:
             return cov.diag().diag()
     return cov
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Deferred test (fast mode): the L x L Cholesky of the gate only DECIDES; the range finder does not need its factor.
+# It runs on a helper stream beside the range finder, which speculates on the usual outcome (test passed); the
+# verdict is read when the basis is ready.  On failure the caller escalates and recomputes -- exactly what the
+# blocking path would have produced.
+# ---------------------------------------------------------------------------------------------------------
+_helper_streams = {}
+
+
+class PendingTest:
+    def __init__(self, info, stream):
+        self.info, self.stream = info, stream
+
+    def passed(self):
+        if self.stream is not None:
+            torch.cuda.current_stream(self.info.device).wait_stream(self.stream)
+        return int(self.info) == 0
+
+
+def repair_deferred(cov):
+    """``repair(cov, "cholesky", assume_asymmetric=True)`` up to and including the launch of the first test:
+    returns (matrix, PendingTest)."""
+    warnings.warn("Estimated covariance matrix was not positive semi-definite. Conveting...")
+    cov = torch.nan_to_num(cov)
+    cov = torch.sqrt(cov * cov.T)
+    if not cov.is_cuda:
+        return cov, PendingTest(torch.linalg.cholesky_ex(cov)[1], None)
+    dev = cov.device
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _helper_streams:
+        _helper_streams[key] = torch.cuda.Stream(dev)
+    helper, main = _helper_streams[key], torch.cuda.current_stream(dev)
+    helper.wait_stream(main)
+    with torch.cuda.stream(helper):
+        info = torch.linalg.cholesky_ex(cov)[1]
+    cov.record_stream(helper)
+    info.record_stream(main)
+    return cov, PendingTest(info, helper)

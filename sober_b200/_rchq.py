@@ -209,8 +209,17 @@ class Recombiner:
             if k_zo_w is not None:
                 gram = gram - k_zo_w @ lm["k_oz"]
             gram = 0.5 * (gram + gram.T)
-            gram = _psd.repair(gram, o.gate, assume_asymmetric=True)
-            U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr, rotate=rotate)
+            if o.gate == "cholesky" and o.defer_gate and o.nystrom_qr != "householder":
+                # the gate's L x L Cholesky only decides: it runs beside the range finder, which speculates on "passed"
+                gram, test = _psd.repair_deferred(gram)
+                probe = _nystrom.draw_test_matrix(gram.shape[-1], n_basis, gram.dtype, gram.device)
+                U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr, rotate=rotate, probe=probe)
+                if not test.passed():
+                    gram = _psd.escalate(gram, o.gate)
+                    U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr, rotate=rotate, probe=probe)
+            else:
+                gram = _psd.repair(gram, o.gate, assume_asymmetric=True)
+                U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr, rotate=rotate)
         else:
             gram = kernel(Z, Z)
             gram = _psd.repair(gram, o.gate)

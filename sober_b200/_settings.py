@@ -39,6 +39,7 @@ class Options:
         self.fused_projection = False  # hand-written DMMA projection+barycentre kernel instead of cuBLAS DGEMM
         self.overlap = os.environ.get("SOBER_B200_OVERLAP", "1") != "0"   # first K1 pass beside the tail of the range finder (two streams); fast mode only
         self.graphs = os.environ.get("SOBER_B200_GRAPHS", "1") != "0"   # replay each Caratheodory step from a CUDA graph
+        self.defer_gate = os.environ.get("SOBER_B200_DEFER_GATE", "1") != "0"   # gate test beside the range finder
         self.rotate_basis = None      # None: rotate the Nystrom basis by its singular vectors unless the null spaces come
                                       # from the projector (then only span(U) matters); True / False force it
         self.stats = None             # optional dict that receives per-stage timings (forces syncs)

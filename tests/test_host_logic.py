@@ -121,6 +121,34 @@ def test_feature_means_preserved_without_remainder():
     assert float((full - sel).abs().max()) < 1e-12
 
 
+@pytest.mark.parametrize("definite", [True, False])
+def test_deferred_gate_equals_blocking_gate(definite):
+    """Fast mode launches the gate's Cholesky test beside the range finder and reads the verdict afterwards; on failure
+    it escalates the jitter and recomputes with the SAME test matrix: identical to the blocking order of operations."""
+    from sober_b200 import _psd
+    g = torch.Generator().manual_seed(4)
+    a = torch.randn(60, 60, dtype=torch.float64, generator=g)
+    sym = a @ a.T / 60 + (0.5 if definite else -0.2) * torch.eye(60, dtype=torch.float64)
+    sym = sym.abs()                                        # the repair takes sqrt(K o K^T) = |K|
+    if not definite:
+        sym[0, 1] = sym[1, 0] = 5.0                        # |K| with a large off-diagonal pair: indefinite
+    assert _psd.passes(sym, "cholesky") == definite
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(9)
+        blocking = _psd.repair(sym.clone(), "cholesky", assume_asymmetric=True)
+        u_blocking = _nystrom.lowrank_basis(blocking, 20, qr="cholqr2", rotate=False)
+        torch.manual_seed(9)
+        deferred, test = _psd.repair_deferred(sym.clone())
+        probe = _nystrom.draw_test_matrix(60, 20, torch.float64, sym.device)
+        u_deferred = _nystrom.lowrank_basis(deferred, 20, qr="cholqr2", rotate=False, probe=probe)
+        assert test.passed() == definite
+        if not test.passed():
+            deferred = _psd.escalate(deferred, "cholesky")
+            u_deferred = _nystrom.lowrank_basis(deferred, 20, qr="cholqr2", rotate=False, probe=probe)
+    assert torch.equal(blocking, deferred) and torch.equal(u_blocking, u_deferred)
+
+
 def test_keepmap_from_device_summary_equals_mask_constructor():
     """KeepMap.from_summary (inclusive cumulative kept-count, as _car._reduce_step returns it) == KeepMap(mask)."""
     g = torch.Generator().manual_seed(1)
