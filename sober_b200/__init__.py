@@ -8,9 +8,10 @@ Importing this package does not need a GPU; calling ``recombination`` does (ther
 from ._rchq import Recombiner, Sharded, SingleProcess, recombination, set_communicator
 from ._settings import configure, options
 from ._install import install, uninstall
+from ._wkde import wkde_pdf
 
 __all__ = ["recombination", "install", "uninstall", "configure", "options", "Recombiner", "Sharded",
-           "SingleProcess", "set_communicator", "enable_sharding"]
+           "SingleProcess", "set_communicator", "enable_sharding", "wkde_pdf"]
 __version__ = "0.1.0"
 
 

@@ -11,6 +11,14 @@ from ._rchq import recombination as _fast
 
 _MODULES = ("SOBER._rchq", "SOBER._sampler", "SOBER.BASQ._basq", "SOBER.FBGP._fully_Bayesian_gp")
 _saved = {}
+_saved_pdf = {}
+
+
+def _kde_pdf(self, X):
+    """Drop-in for ``WeightedKernelDensityEstimation.pdf`` (SOBER/_wkde.py:109-145): same values, returned where and
+    as what the estimator keeps its own tensors."""
+    from ._wkde import pdf_of
+    return pdf_of(self, X).to(device=self.weights.device, dtype=self.weights.dtype)
 
 
 def install(package="SOBER"):
@@ -23,6 +31,14 @@ def install(package="SOBER"):
             _saved[name] = mod.recombination
             mod.recombination = _fast
             patched.append(name)
+    # the weighted-KDE density shares K1: patch the class method if the module is loaded
+    name = package + "._wkde"
+    mod = sys.modules.get(name)
+    cls = getattr(mod, "WeightedKernelDensityEstimation", None) if mod is not None else None
+    if cls is not None and getattr(cls, "pdf", None) is not _kde_pdf:
+        _saved_pdf[name] = cls.pdf
+        cls.pdf = _kde_pdf
+        patched.append(name + ".WeightedKernelDensityEstimation.pdf")
     return patched
 
 
@@ -32,3 +48,8 @@ def uninstall():
         if mod is not None:
             mod.recombination = fn
         del _saved[name]
+    for name, fn in list(_saved_pdf.items()):
+        mod = sys.modules.get(name)
+        if mod is not None:
+            mod.WeightedKernelDensityEstimation.pdf = fn
+        del _saved_pdf[name]
