@@ -241,6 +241,14 @@ int sober_cholesky_upper_fits(int32_t q);
 int sober_cholesky_upper(const double* G, int64_t ldg, int32_t q, double* R, int64_t ldr, int32_t* info, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Assignment step of Lloyd's k-means (SOBER/_weights.py:100-126, the KMeans that produces the Nystrom landmarks,
+ * SOBER/_sampler.py:316-317):  labels[i] = argmin_k sum_j (X[i,j] - C[k,j])^2, first minimum on ties, first NaN wins
+ * (torch.argmin).  X: n x d (ldx), C: K x d contiguous, d <= 16; labels: n int64.  Nothing of size n*K is stored.
+ * ------------------------------------------------------------------------------------------------- */
+int sober_kmeans_assign(const double* X, int64_t ldx, int64_t n, int32_t d, const double* C, int32_t K, int64_t* labels,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Stream confined to all SMs of the current device but `reserve_sms` (a CUDA green context; created on first use,
  * cached, never destroyed).  Work launched on it leaves the reserved SMs to the other streams: the first K1 pass runs
  * there beside the one-CTA kernels of the Nystrom range finder.  *stream = NULL when the driver cannot partition the

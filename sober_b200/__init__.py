@@ -9,9 +9,10 @@ from ._rchq import Recombiner, Sharded, SingleProcess, recombination, set_commun
 from ._settings import configure, options
 from ._install import install, uninstall
 from ._wkde import wkde_pdf
+from ._kmeans import kmeans
 
 __all__ = ["recombination", "install", "uninstall", "configure", "options", "Recombiner", "Sharded",
-           "SingleProcess", "set_communicator", "enable_sharding", "wkde_pdf"]
+           "SingleProcess", "set_communicator", "enable_sharding", "wkde_pdf", "kmeans"]
 __version__ = "0.1.0"
 
 

@@ -12,6 +12,14 @@ from ._rchq import recombination as _fast
 _MODULES = ("SOBER._rchq", "SOBER._sampler", "SOBER.BASQ._basq", "SOBER.FBGP._fully_Bayesian_gp")
 _saved = {}
 _saved_pdf = {}
+_saved_fn = {}
+
+
+def _kmeans(x, K=10, Niter=10):
+    """Drop-in for ``KMeans`` (SOBER/_weights.py:100-126): same (labels, centroids), on x's device and dtype."""
+    from ._kmeans import kmeans
+    cl, c = kmeans(x, K, Niter)
+    return cl.to(x.device), c.to(device=x.device, dtype=x.dtype)
 
 
 def _kde_pdf(self, X):
@@ -39,10 +47,22 @@ def install(package="SOBER"):
         _saved_pdf[name] = cls.pdf
         cls.pdf = _kde_pdf
         patched.append(name + ".WeightedKernelDensityEstimation.pdf")
+    # k-means landmark selection: kmeans_resampling looks KMeans up in its module globals
+    name = package + "._weights"
+    mod = sys.modules.get(name)
+    if mod is not None and hasattr(mod, "KMeans") and mod.KMeans is not _kmeans:
+        _saved_fn[name] = mod.KMeans
+        mod.KMeans = _kmeans
+        patched.append(name + ".KMeans")
     return patched
 
 
 def uninstall():
+    for name, fn in list(_saved_fn.items()):
+        mod = sys.modules.get(name)
+        if mod is not None:
+            mod.KMeans = fn
+        del _saved_fn[name]
     for name, fn in list(_saved.items()):
         mod = sys.modules.get(name)
         if mod is not None:

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "sober_fp64_probe": (C.c_int, [_I32, _I64, _P, _P]),
     "sober_cholesky_upper_fits": (C.c_int, [_I32]),
     "sober_cholesky_upper": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _P]),
+    "sober_kmeans_assign": (C.c_int, [_P, _I64, _I64, _I32, _P, _I32, _P, _P]),
     "sober_partition_stream": (C.c_int, [_I32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "sober_dmma_probe": (C.c_int, [_I32, _I64, _P, _P]),
 }

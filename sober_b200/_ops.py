@@ -330,6 +330,20 @@ class CudaOps:
                                                 self._stream()), "scatter_result")
         self.launches += 1
 
+    def kmeans_assign(self, X, centroids):
+        """labels (n,) int64: nearest centroid of every row of X (n x d, d <= 16); first minimum on ties."""
+        n, d = X.shape
+        K = centroids.shape[0]
+        assert X.stride(1) == 1 and centroids.is_contiguous() and centroids.shape[1] == d
+        labels = torch.empty(n, dtype=torch.int64, device=self.device)
+        with self._guard():
+            t0 = self._begin("kmeans_assign")
+            check(self.lib.sober_kmeans_assign(_ptr(X), X.stride(0), n, d, _ptr(centroids), K, _ptr(labels),
+                                               self._stream()), "kmeans_assign")
+            self._end("kmeans_assign", t0, n * K)
+        self.launches += 1
+        return labels
+
     def partition_stream(self):
         """Stream confined to all SMs but ``SOBER_B200_RESERVE_SMS`` (default 8), or None when the driver cannot
         partition the device (include/sober_b200.h: sober_partition_stream)."""

@@ -130,6 +130,13 @@ class TorchOps:
             rec_out[:, d + 1] = mu_out
         return idx_out, mu_out, rec_out
 
+    def kmeans_assign(self, X, centroids, chunk=4096):
+        out = torch.empty(X.shape[0], dtype=torch.int64)
+        for s in range(0, X.shape[0], chunk):
+            d2 = ((X[s:s + chunk, None, :] - centroids[None, :, :]) ** 2).sum(-1)
+            out[s:s + chunk] = d2.argmin(1)
+        return out
+
     def scatter_result(self, dst, idx, w):
         dst.zero_()
         dst[idx] = w
