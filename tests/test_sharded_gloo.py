@@ -49,3 +49,44 @@ def test_two_rank_shard_equals_single_process(name, split):
     if m0 is not None:                                           # each rank's weight shard holds its part
         merged = torch.cat([m0, m1])
         assert float((merged - torch.from_numpy(case.raw["mu_after"])).abs().max()) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------------------
+# k-means landmark selection: rows sharded, one all-reduce of sums and counts per iteration
+# ------------------------------------------------------------------------------------------------------------
+def _kmeans_worker(rank, world, port, split, out):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _cpu_ops import TorchOps
+    from sober_b200 import Sharded
+    from sober_b200._kmeans import kmeans
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        x = torch.rand(6000, 4, dtype=torch.float64, generator=torch.Generator().manual_seed(11))
+        lo, hi = (0, split) if rank == 0 else (split, len(x))
+        cl, c = kmeans(x[lo:hi].clone(), K=40, Niter=6, ops=TorchOps(), comm=Sharded())
+        out[rank] = (cl.clone(), c.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("split", [3000, 17, 0])
+def test_two_rank_kmeans_equals_single_process(split):
+    """split = 17: the first K = 40 rows (the initial centroids) straddle the two ranks; split = 0: an empty shard."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from _cpu_ops import TorchOps
+    from sober_b200._kmeans import kmeans
+    port = 31500 + (os.getpid() + split) % 2000
+    manager = mp.Manager()
+    out = manager.dict()
+    mp.spawn(_kmeans_worker, args=(2, port, split, out), nprocs=2, join=True)
+    x = torch.rand(6000, 4, dtype=torch.float64, generator=torch.Generator().manual_seed(11))
+    cl, c = kmeans(x, K=40, Niter=6, ops=TorchOps())
+    (cl0, c0), (cl1, c1) = out[0], out[1]
+    assert torch.equal(c0, c1)
+    assert float((c0 - c).abs().max()) < 1e-12
+    assert torch.equal(torch.cat([cl0, cl1]), cl)
