@@ -28,7 +28,10 @@ _MAX_QUERIES = 1 << 24  # per launch (grid.y limit of K1: 65535 * 512 landmarks)
 def wkde_pdf(centres, weights, covariance, queries, bounds=None, constant=None, ops=None):
     """centres (n_kde, d), weights (n_kde,), covariance (d, d), queries (N, d) -> densities (N,) float64 on the device.
     ``bounds`` (2, d): queries outside get 0 (SOBER/_wkde.py:131-136); ``constant`` (n_kde,): per-centre truncation
-    constants dividing the weights (``compute_cdf=True``, :138-139)."""
+    constants dividing the weights (``compute_cdf=True``, :138-139).
+    ``covariance`` must be symmetric positive definite, as the estimator's is after the gate it passes at construction
+    (``_compute_covariance``, :98-107); the second, idempotent pass of that gate inside ``safe_mvn_register``
+    (SOBER/_utils.py:159-169) is therefore not repeated here."""
     if ops is None:
         from ._rchq import _ops
         ops = _ops()
