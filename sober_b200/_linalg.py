@@ -19,13 +19,17 @@ _NO_GUARD = contextlib.nullcontext()
 launches = 0   # kernels launched from this module (bench.py adds them to its gpu_launches claim)
 
 
+_get_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda i: torch.cuda.current_stream(i).cuda_stream)
+_current_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+
+
 def _raw_stream(device):
     index = device.index if device.index is not None else torch.cuda.current_device()
-    return index, C.c_void_p(torch._C._cuda_getCurrentRawStream(index))
+    return index, C.c_void_p(_get_raw_stream(index))
 
 
 def _guard(device, index):
-    return _NO_GUARD if torch._C._cuda_getDevice() == index else torch.cuda.device(device)
+    return _NO_GUARD if _current_device() == index else torch.cuda.device(device)
 
 
 def cholesky_upper(g):

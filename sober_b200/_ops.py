@@ -49,6 +49,11 @@ class LandmarkTable:
 
 _NO_GUARD = contextlib.nullcontext()
 
+# raw equivalents of torch.cuda.current_stream(i).cuda_stream / torch.cuda.current_device() (private but stable since
+# torch 1.x; the public calls are used if a build lacks them)
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or (lambda i: torch.cuda.current_stream(i).cuda_stream)
+_current_device = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+
 
 class CudaOps:
     def __init__(self, device=None):
@@ -68,14 +73,14 @@ class CudaOps:
     # GPU idle: torch.cuda.current_stream() (8 us: builds a Stream object) and the torch.cuda.device() guard (7 us)
     # are replaced by their raw equivalents.
     def _stream_ptr(self):
-        return torch._C._cuda_getCurrentRawStream(self.index)
+        return _raw_stream(self.index)
 
     def _stream(self):
-        return C.c_void_p(torch._C._cuda_getCurrentRawStream(self.index))
+        return C.c_void_p(_raw_stream(self.index))
 
     def _guard(self):
         """Device guard that costs nothing when the current device already is ours (one process per GPU)."""
-        if torch._C._cuda_getDevice() == self.index:
+        if _current_device() == self.index:
             return _NO_GUARD
         return torch.cuda.device(self.device)
 
