@@ -112,7 +112,8 @@ int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_out, double*
  *   LUT family), lut as described at the enum.
  * At: S x L (transposed on purpose: coalesced stores and it is the left operand of the projection).
  * workspace holds the per-split partial sums (deterministic two-stage reduction, no atomics).
- * variant: 0 = automatic (records -> register kernel, else tiled), 1 = force the generic tiled kernel.
+ * variant: 0 = automatic (records -> register kernel, else tiled), 1 = force the generic tiled kernel,
+ *          2 = EXPERIMENTAL record kernel without the per-chunk block barrier (empty-mbarrier pipeline, 4 stages).
  * ------------------------------------------------------------------------------------------------- */
 typedef struct sober_group_args {
     const double* X;

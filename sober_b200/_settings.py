@@ -35,7 +35,8 @@ class Options:
         self.set_mode(mode or os.environ.get("SOBER_B200_MODE", "fast"))
         self.fuse = True              # introspect Kernel objects; False forces the generic-callable path
         self.generic_chunk = 1 << 16  # candidates per Gram tile on the generic path
-        self.k1_variant = 0           # 0 auto (record / bit-packed kernels when they apply), 1 force the tiled kernel
+        self.k1_variant = 0           # 0 auto (record / bit-packed kernels when they apply), 1 force the tiled kernel,
+                                      # 2 experimental barrier-free record kernel (not yet validated on hardware)
         self.fused_projection = False  # hand-written DMMA projection+barycentre kernel instead of cuBLAS DGEMM
         self.overlap = os.environ.get("SOBER_B200_OVERLAP", "1") != "0"   # first K1 pass beside the tail of the range finder (two streams); fast mode only
         self.graphs = os.environ.get("SOBER_B200_GRAPHS", "1") != "0"   # replay each Caratheodory step from a CUDA graph

@@ -50,11 +50,18 @@ constexpr int REC_STAGES = 3;
 #ifndef SOBER_REC_MINB
 #define SOBER_REC_MINB 2
 #endif
-template <int D, int FAM, int TL, int TG, bool UNIT>
+// NB (variant 2, EXPERIMENTAL, opt-in through sober_group_args.variant / options.k1_variant = 2, not yet run on
+// hardware): no block barrier per chunk.  Each warp releases a stage by arriving on its "empty" mbarrier; thread 0
+// refills the stage of chunk c-1 after finishing chunk c (one chunk of slack, hence 4 stages instead of 3), so no warp
+// ever waits for the slowest one -- the barrier stall is 0.7 of 6.3 stall cycles per issue in the ncu profile of the
+// default kernel.  NB = false compiles to the same instructions as before the parameter existed.
+template <int D, int FAM, int TL, int TG, bool UNIT, bool NB = false>
 __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_kernel(const GroupParams p) {
     constexpr int LDR = (D + 3) / 2 * 2;  // d + 2 rounded up to even
+    constexpr int REC_STAGES = NB ? 4 : sober::REC_STAGES;
     __shared__ __align__(16) double buf[REC_STAGES][REC_ROWS][TG][LDR];
     __shared__ __align__(8) uint64_t bars[REC_STAGES];
+    __shared__ __align__(8) uint64_t empty[NB ? REC_STAGES : 1];
     __shared__ double tab[EXP_TAB_SIZE];
 
     const int t = threadIdx.x;
@@ -68,6 +75,8 @@ __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_ker
     asm volatile("" : "+r"(tab_s));   // opaque: otherwise the address is re-derived (S2UR + ULEA + ...) at every use
     if (t == 0) {
         for (int s = 0; s < REC_STAGES; ++s) mbar_init(&bars[s], 1);
+        if (NB)
+            for (int s = 0; s < REC_STAGES; ++s) mbar_init(&empty[s], REC_WARPS);
         mbar_fence_init();
     }
     __syncthreads();
@@ -193,8 +202,17 @@ __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_ker
                 }
             }
         }
-        __syncthreads();   // every warp is done with this stage before it is refilled
-        if (t == 0 && c + REC_STAGES < nchunks) issue(c + REC_STAGES);
+        if (NB) {
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&empty[stage])) : "memory");
+            if (t == 0 && c >= 1 && c - 1 + REC_STAGES < nchunks) {
+                mbar_wait(&empty[(c - 1) % REC_STAGES], (uint32_t)(((c - 1) / REC_STAGES) & 1));   // all 8 warps left it
+                issue(c - 1 + REC_STAGES);
+            }
+        } else {
+            __syncthreads();   // every warp is done with this stage before it is refilled
+            if (t == 0 && c + REC_STAGES < nchunks) issue(c + REC_STAGES);
+        }
     }
 
     double* out = p.out + (int64_t)blockIdx.z * p.S * p.L;
@@ -522,6 +540,7 @@ static int bits_tl(int W) { return W <= 8 ? 4 : (W <= 16 ? 2 : 1); }
 
 struct Plan {
     bool records;
+    bool no_barrier;   // experimental K1 variant 2
     bool bits;
     dim3 grid, block;
     int nsplit;
@@ -535,6 +554,7 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
     pl->row_end = a->n_local > 0 ? ceil_div(hi, a->S) : pl->row_begin;
     const int64_t rows = pl->row_end - pl->row_begin;
     pl->records = a->rec != nullptr && a->variant != 1;
+    pl->no_barrier = a->variant == 2;
     pl->bits = a->family == SOBER_TANIMOTO_BITS || a->family == SOBER_HAMMING_LUT;
     if (a->family == SOBER_HAMMING_LUT && !a->lut) return false;
     if (pl->bits) {
@@ -572,7 +592,12 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
 
 template <int D, int FAM>
 static void launch_records(const Plan& pl, const GroupParams& p, cudaStream_t st) {
-    if (p.unit_weights)
+    if (pl.no_barrier) {   // experimental variant 2
+        if (p.unit_weights)
+            group_records_kernel<D, FAM, REC_TL, REC_TG, true, true><<<pl.grid, pl.block, 0, st>>>(p);
+        else
+            group_records_kernel<D, FAM, REC_TL, REC_TG, false, true><<<pl.grid, pl.block, 0, st>>>(p);
+    } else if (p.unit_weights)
         group_records_kernel<D, FAM, REC_TL, REC_TG, true><<<pl.grid, pl.block, 0, st>>>(p);
     else
         group_records_kernel<D, FAM, REC_TL, REC_TG, false><<<pl.grid, pl.block, 0, st>>>(p);
