@@ -168,7 +168,10 @@ def reduce_step(ops, feats, mass, use_graph=True):
             entry = _graphs[key] = _ReduceGraph(ops, feats, mass)
             # kernels of ours inside the graph (bench.py's launch count): replays run them without passing the wrappers
             entry.launches = (ops.launches - before, _linalg.launches - before_la)
-        except Exception:                               # capture unsupported here: stay eager
+        except Exception as err:                        # capture unsupported here: stay eager, but say so once
+            import warnings
+            warnings.warn("sober_b200: CUDA-graph capture of the Caratheodory step failed (%s); running it eagerly"
+                          % (str(err).splitlines()[0] if str(err) else type(err).__name__))
             _graphs[key] = "eager"
             ops.launches, _linalg.launches = before, before_la
             return _reduce_step(ops, feats, mass)
