@@ -1,17 +1,27 @@
 #!/usr/bin/env python
 """Benchmark of the RCHQ batch-selection hot path (BASELINE.json metric: recombination candidates/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c5|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|c1..c5]
 
 One "step" = one full ``recombination(...)`` call (Nystrom block + all grouped passes + CAR + compaction) over one
-batch of synthetic candidates.  Default workload = BASELINE.json configs[1] (Hartmann-6D shape: n_rec = 1e6 per
-GPU, n_nys = 1000, batch = 200, Matern-5/2, float64).  With N > 1 (torchrun, one rank per GPU) the candidates are
-row-sharded, n_rec = 1e6 PER GPU (weak scaling); the one collective per iteration is the all-reduce of the group
-sums.  Rank 0 prints ONE JSON line.
+batch of synthetic candidates.
+
+Workload (``--workload auto``, what the driver runs):
+  N = 1  BASELINE.json configs[1] (C2, Hartmann-6D shape: n_rec = 1e6, n_nys = 1000, batch = 200, Matern-5/2, f64); the
+         line also carries a ``c5`` block (the north_star target config on this one GPU), a ``parity`` block (fast mode
+         vs the CPU oracle on a 1e5-candidate sample of the workload: indices / weights / MMD), ``parity_mode`` (ms per
+         step of the mode that reproduces the reference's op sequence) and ``reference_gpu`` (the reference algorithm's
+         own PyTorch path -- oracle port -- executing on this GPU).
+  N > 1  BASELINE.json configs[4] (C5, the north_star target: n_rec = 1e7 TOTAL, n_nys = 2000, batch = 1000), STRONG
+         scaling: candidates row-sharded over the ranks, one all-reduce of the group sums per iteration; the line also
+         carries ``c5_1gpu`` (the same config on rank 0 alone, measured in the same run) and ``weak_c2`` (C2 with 1e6
+         candidates per GPU).
+Rank 0 prints ONE JSON line.
 
 ``--impl reference`` times the reference algorithm's CPU path (the oracle restatement of SOBER/_rchq.py, which is
-bit-identical to it; the reference itself is Python and /root/reference does not exist on the GPU box) on a
-bounded sample of the same workload with all host threads.
+bit-identical to it; the reference itself is Python and /root/reference does not exist on the GPU box) with all host
+threads: on the full workload when the host has the memory for the reference's materialised (E, L, S) Gram
+(40 B x N x n_nys), else on a bounded sample of it (``extrapolated: true``).
 """
 import argparse
 import json
@@ -26,9 +36,6 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
 
 WORKLOADS = {
     # name: (n_rec per GPU, d, n_nys, batch, family, lengthscale, description)
@@ -68,7 +75,6 @@ def make_kernel(name, device, pred_cov=False):
     if not pred_cov:
         return ok.Kernel(ok.BareModel(cov), mode="kernel")
     # the default Sober kernel: GP posterior predictive covariance with a synthetic GP of 200 observations
-    g = torch.Generator().manual_seed(5)
     x_obs = synth(name, 200, 5, torch.device("cpu"))[0].to(device)
     return ok.Kernel(ok.GPModel(cov, x_obs, None, noise=1e-4), mode="predictive_covariance")
 
@@ -113,8 +119,8 @@ class ClockSampler:
 
 
 def cpu_reference_rate(name, sample_n, steps, warmup, threads):
-    """The reference algorithm on the host cores: oracle/rchq.py (bit-identical to SOBER/_rchq.py on the CPU) on a
-    bounded sample of the workload.  Returns candidates/sec (best step) and the per-step seconds."""
+    """The reference algorithm on the host cores: oracle/rchq.py (bit-identical to SOBER/_rchq.py on the CPU) on
+    ``sample_n`` candidates of the workload.  Returns candidates/sec (best step) and the per-step seconds."""
     from oracle import rchq
     torch.set_num_threads(threads)
     _, d, L, b, fam, ls, _ = WORKLOADS[name]
@@ -137,45 +143,283 @@ def cpu_reference_rate(name, sample_n, steps, warmup, threads):
     return sample_n / min(times), times
 
 
+def host_memory_available():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return 0
+
+
+def reference_arm(args, name, threads):
+    """``--impl reference``: the reference algorithm's CPU path on this box's host cores."""
+    n_rec, d, L, b, fam, ls, desc = WORKLOADS[name]
+    # the reference materialises the (E, L, S) Gram and a few temporaries of its size: ~40 B x N x n_nys (SURVEY 8d)
+    need = 48 * n_rec * L
+    full = args.cpu_sample <= 0 and host_memory_available() > need + (16 << 30) and name in ("c1", "c2", "c3")
+    sample = n_rec if full else min(args.cpu_sample if args.cpu_sample > 0 else 100_000, n_rec)
+    steps, warm = max(1, min(args.steps, 2 if full else 3)), (0 if full else min(args.warmup, 1))
+    rate, times = cpu_reference_rate(name, sample, steps, warm, threads)
+    what = ("oracle/rchq.py (bit-identical restatement of SOBER/_rchq.py) on %s of the workload's %d candidates, full "
+            "n_nys/batch, torch CPU f64, %d threads; the reference materialises the (E,L,S) Gram so its memory grows as "
+            "40 B x N x n_nys" % ("ALL" if sample == n_rec else "%d" % sample, n_rec, threads))
+    print(json.dumps({
+        "impl": "reference", "metric": "recombination candidates/sec", "value": rate, "unit": "candidates/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * min(times),
+        "higher_is_better": True, "scaling": "strong" if name == "c5" else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "n_nys": L, "batch": b, "kernel": fam, "sample_n_rec": sample,
+                   "extrapolated": sample != n_rec,
+                   "extrapolation": None if sample == n_rec else
+                   "candidates/s measured on the sample; the reference's time is linear in N x n_nys (84 % kernel "
+                   "evaluations, SURVEY.md section 6), its memory too -- the full size does not fit this host"},
+        "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": threads, "kind": "port", "sample": what},
+        "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------
+class Runner:
+    """One workload on this rank's device: data, kernel object, the timed loops."""
+
+    def __init__(self, name, dev, rank, world, pred_cov=False, sharded=True, n_override=None):
+        import sober_b200
+        self.sb = sober_b200
+        self.name, self.dev, self.rank, self.world = name, dev, rank, (world if sharded else 1)
+        n_rec, self.d, self.L, self.b, self.fam, self.ls, self.desc = WORKLOADS[name]
+        self.strong = name == "c5"
+        self.n_local = n_override or (n_rec // self.world if self.strong else n_rec)
+        self.n_total = self.n_local * self.world
+        self.X, self.mu = synth(name, self.n_local, 100 + (rank if sharded else 0), dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            tot = self.mu.sum()
+            dist.all_reduce(tot)
+            self.mu /= tot
+        else:
+            self.mu /= self.mu.sum()
+        # landmarks: replicated; drawn from rank 0's shard and broadcast
+        gen = torch.Generator(device=dev).manual_seed(1)
+        self.Z = self.X[torch.randperm(self.n_local, device=dev, generator=gen)[:self.L]].clone()
+        if self.world > 1:
+            dist.broadcast(self.Z, 0)
+        self.kern = make_kernel(name, dev, pred_cov)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(self.dev)
+
+    def step(self, weights, X=None):
+        torch.manual_seed(7)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return self.sb.recombination(self.X if X is None else X, self.Z, self.b, self.kern, self.dev,
+                                         torch.float64, init_weights=weights)
+
+    def max_over_ranks(self, ms):
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    def timed(self, steps, warmup, flush, ops=None):
+        """W untimed + K timed steps, inputs resident in HBM; CUDA events on the launching stream, barrier + synchronize
+        on both sides, max over ranks.  Returns (ms total, idx, w)."""
+        for _ in range(warmup):
+            flush.zero_()
+            idx, w = self.step(self.mu.clone())
+        self.barrier()
+        if ops is not None:
+            ops.timing = {}
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        t_start.record()
+        for _ in range(steps):
+            flush.zero_()
+            idx, w = self.step(self.mu.clone())
+        t_end.record()
+        self.barrier()
+        ms = self.max_over_ranks(t_start.elapsed_time(t_end))
+        assert len(idx) <= self.b and abs(float(w.sum()) - 1.0) < 1e-9, "benchmark result failed its invariants"
+        return ms, idx, w
+
+    def timed_e2e(self, steps, flush):
+        """The same metric through the public API with HOST buffers: pinned inputs, host->device copies of the
+        candidates and weights and the device->host read of (idx, w) inside the timed region, every step."""
+        Xh, muh = self.X.cpu().pin_memory(), self.mu.cpu().pin_memory()
+        wh = torch.empty_like(muh).pin_memory()
+        for _ in range(2):
+            wh.copy_(muh)
+            idx_e, w_e = self.step(wh, Xh)
+        self.barrier()
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_ev.record()
+        for _ in range(steps):
+            flush.zero_()
+            wh.copy_(muh)
+            idx_e, w_e = self.step(wh, Xh)
+            idx_host, w_host = idx_e.cpu(), w_e.cpu()
+        e_ev.record()
+        self.barrier()
+        ms = self.max_over_ranks(s_ev.elapsed_time(e_ev))
+        return ms, Xh.numel() * 8 + muh.numel() * 8, idx_host.numel() * 8 + w_host.numel() * 8
+
+
+def parity_block(runner, sample_n):
+    """Fast mode (the benchmarked mode) against the CPU oracle on a sample of the workload: the oracle gets the same
+    test matrix for the randomised range finder and the fast mode's null-space construction restated with LAPACK
+    (oracle.projector_nullspace) -- SURVEY.md TL;DR 3 and 7: both are free choices of the reference's algorithm that
+    decide which vertex it walks to.  Returns the block for the JSON line."""
+    from oracle import rchq as oracle
+    from sober_b200 import _nystrom
+    name, dev = runner.name, runner.dev
+    _, d, L, b, fam, ls, _ = WORKLOADS[name]
+    cpu = torch.device("cpu")
+    X, mu = synth(name, sample_n, 0, cpu)
+    mu /= mu.sum()
+    Z = X[torch.randperm(sample_n, generator=torch.Generator().manual_seed(1))[:L]].clone()
+    R = torch.randn(L, b - 1, dtype=torch.float64, generator=torch.Generator().manual_seed(5))
+    kern_cpu = make_kernel(name, cpu)
+    orig = torch.randn
+    torch.randn = lambda *a, **k: R.clone() if tuple(a[:2]) == tuple(R.shape) else orig(*a, **k)
+    t0 = time.perf_counter()
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            m_o = mu.clone()
+            idx_o, w_o = oracle.recombination(X, Z, b, kern_cpu, None, None, init_weights=m_o,
+                                              nullspace=oracle.projector_nullspace)
+    finally:
+        torch.randn = orig
+    t_oracle = time.perf_counter() - t0
+    _nystrom._injected_test_matrix = R
+    try:
+        with warnings.catch_warnings(), runner.sb.configure(mode="fast"):
+            warnings.simplefilter("ignore")
+            m_g = mu.clone().to(dev)
+            idx_g, w_g = runner.sb.recombination(X.to(dev), Z.to(dev), b, runner.kern, dev, torch.float64,
+                                                 init_weights=m_g)
+    finally:
+        _nystrom._injected_test_matrix = None
+    torch.cuda.synchronize(dev)
+    same = bool(torch.equal(idx_g.cpu(), idx_o))
+    common = sorted(set(idx_g.cpu().tolist()) & set(idx_o.tolist()))
+    out = {"mode": "fast", "n": sample_n, "n_nys": L, "batch": b, "indices_identical": same,
+           "points": int(len(idx_o)), "points_in_common": len(common),
+           "oracle": "oracle/rchq.py on the CPU, same test matrix, nullspace=oracle.projector_nullspace",
+           "oracle_seconds": t_oracle}
+    if same:
+        out["max_dw"] = float((w_g.cpu() - w_o).abs().max())
+        out["max_dmu_in_place"] = float((m_g.cpu() - m_o).abs().max())
+    # worst-case quadrature error of both batches (SURVEY 8c), on the device with the kernel callable
+    Xd, mud = X.to(dev), mu.to(dev)
+    mmd_o = float(oracle.mmd_squared(runner.kern, Xd, mud, idx_o.to(dev), w_o.to(dev), chunk=8192))
+    mmd_g = float(oracle.mmd_squared(runner.kern, Xd, mud, idx_g, w_g.to(torch.float64), chunk=8192))
+    out["mmd2_oracle"], out["mmd2_ours"] = mmd_o, mmd_g
+    out["mmd_rel"] = abs(mmd_g - mmd_o) / abs(mmd_o) if mmd_o != 0 else None
+    out["ok"] = bool(same and out["max_dw"] < 1e-6 and out["mmd_rel"] is not None and out["mmd_rel"] < 1e-6)
+    return out
+
+
+def reference_gpu_leg(runner, flush):
+    """The reference algorithm's own PyTorch path (oracle port, op for op SOBER/_rchq.py) executing on THIS GPU on the
+    full workload (the same-box comparison).  One warm-up on a small sample, one timed call."""
+    from oracle import rchq as oracle
+    dev = runner.dev
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            torch.manual_seed(7)
+            n_small = min(20_000, runner.n_local)
+            oracle.recombination(runner.X[:n_small], runner.Z, runner.b, runner.kern, dev, None,
+                                 init_weights=runner.mu[:n_small].clone())
+            torch.cuda.synchronize(dev)
+            flush.zero_()
+            torch.manual_seed(7)
+            w0 = runner.mu.clone()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            idx, w = oracle.recombination(runner.X, runner.Z, runner.b, runner.kern, dev, None, init_weights=w0)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+        peak = torch.cuda.max_memory_allocated(dev)
+        return {"value": runner.n_local / dt, "unit": "candidates/s", "ms_per_step": 1e3 * dt, "steps": 1,
+                "kind": "oracle/rchq.py (port of SOBER/_rchq.py) with device=cuda: torch ops -> cuBLAS / cuSOLVER / ATen",
+                "peak_device_bytes": int(peak), "points": int(len(idx))}
+    except Exception as err:            # e.g. out of memory for the materialised (E, L, S) Gram
+        torch.cuda.empty_cache()
+        return {"unavailable": "%s: %s" % (type(err).__name__, str(err).splitlines()[0][:160] if str(err) else "")}
+
+
+def fp64_peak(ops):
+    """FP64 FMA peak of this GPU (not in MEASURED_PEAKS.json): dependent-chain DFMA probe, 2 flop per FMA."""
+    iters, blocks = 1 << 16, 148 * 8
+    for _ in range(2):
+        ops.fp64_probe(blocks, iters)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    ops.fp64_probe(blocks, iters)
+    p1.record()
+    torch.cuda.synchronize()
+    return blocks * 256 * iters * 16 / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+
+def popc_peak(ops):
+    """Integer-pipe peak in 64-bit AND+POPC word-ops per second (the unit of the bit-packed K1 kernels)."""
+    iters, blocks = 1 << 16, 148 * 8
+    for _ in range(2):
+        ops.popc_probe(blocks, iters)
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    ops.popc_probe(blocks, iters)
+    p1.record()
+    torch.cuda.synchronize()
+    return blocks * 256 * iters * 4 / (p0.elapsed_time(p1) * 1e-3) / 1e9
+
+
+def measured_traffic(name, world, pred_cov):
+    """DRAM bytes of the largest K1 launch from the committed ncu --set full capture of this shape
+    (profiles/k1_traffic.json, written by tools/ncu_pick.py from the .ncu-rep of the round), or None."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+        rec = table.get("%s_%dgpu%s" % (name, world, "_predcov" if pred_cov else ""))
+        return (rec["dram_bytes"], rec["source"]) if rec else (None, None)
+    except Exception:
+        return None, None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS))
     ap.add_argument("--mode", default="fast", choices=["fast", "parity"])
-    ap.add_argument("--cpu-sample", type=int, default=100_000)
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="candidates of the CPU reference runs; 0 = automatic (1e5 for cpu_baseline / parity; the "
+                         "reference arm takes the full workload when the host memory allows)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c5 / parity / parity_mode / reference_gpu blocks")
     ap.add_argument("--pred-cov", action="store_true",
                     help="use Kernel(model, 'predictive_covariance') with a synthetic 200-observation GP (SURVEY 8d)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    name = args.workload
+    name = args.workload if args.workload != "auto" else ("c2" if world == 1 else "c5")
     n_rec, d, L, b, fam, ls, desc = WORKLOADS[name]
     threads = os.cpu_count() or 1
 
-    # --------------------------------------------------------------------------------------------------
     if args.impl == "reference":
-        if rank != 0:
-            return
-        sample = min(args.cpu_sample, n_rec)
-        steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
-        rate, times = cpu_reference_rate(name, sample, steps, warm, threads)
-        print(json.dumps({
-            "impl": "reference", "metric": "recombination candidates/sec", "value": rate, "unit": "candidates/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * min(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "n_nys": L, "batch": b, "kernel": fam, "sample_n_rec": sample},
-            "cpu_baseline": {"value": rate, "unit": "candidates/s", "cores": threads, "kind": "port",
-                             "sample": "oracle/rchq.py (bit-identical restatement of SOBER/_rchq.py) on %d of the "
-                                       "workload's candidates, full n_nys/batch, torch CPU f64, %d threads; the "
-                                       "reference materialises the (E,L,S) Gram so its memory grows as 40 B x N x "
-                                       "n_nys" % (sample, threads)},
-            "e2e": {"value": rate, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        if rank == 0:
+            reference_arm(args, name, threads)
         return
 
     # --------------------------------------------------------------------------------------------------
@@ -186,174 +430,130 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         sober_b200.enable_sharding()
-    strong = name == "c5"
-    n_local = n_rec // world if strong else n_rec
-    n_total = n_local * world
-    X, mu = synth(name, n_local, 100 + rank, dev)
-    if world > 1:
-        tot = mu.sum()
-        dist.all_reduce(tot)
-        mu /= tot
-    else:
-        mu /= mu.sum()
-    # landmarks: replicated; drawn from rank 0's shard and broadcast
-    Z = X[torch.randperm(n_local, device=dev, generator=torch.Generator(device=dev).manual_seed(1))[:L]].clone()
-    if world > 1:
-        dist.broadcast(Z, 0)
-    kern = make_kernel(name, dev, args.pred_cov)
-    from sober_b200 import _rchq
+    from sober_b200 import _rchq, _linalg
     ops = _rchq._ops()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def step(weights):
-        torch.manual_seed(7)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            return sober_b200.recombination(X, Z, b, kern, dev, torch.float64, init_weights=weights)
-
     sober_b200.options.set_mode(args.mode)
-    for _ in range(args.warmup):
-        flush.zero_()
-        idx, w = step(mu.clone())
-    barrier()
+    run = Runner(name, dev, rank, world, args.pred_cov)
 
     # ---- timed region: K steps, inputs resident in HBM ----
-    ops.timing = {}
-    from sober_b200 import _linalg
+    launches0 = ops.launches + _linalg.launches
+    for _ in range(args.warmup):
+        flush.zero_()
+        run.step(run.mu.clone())
     launches0 = ops.launches + _linalg.launches
     with ClockSampler(local_rank) as clocks:
-        barrier()
-        t_start = torch.cuda.Event(enable_timing=True)
-        t_end = torch.cuda.Event(enable_timing=True)
-        t_start.record()
-        for _ in range(args.steps):
-            flush.zero_()
-            idx, w = step(mu.clone())
-        t_end.record()
-        barrier()
-    elapsed_ms = t_start.elapsed_time(t_end)
+        elapsed_ms, idx, w = run.timed(args.steps, 0, flush, ops)
     timing = ops.timing_summary()
     uc_big = ops.timing_largest("update_compact")
     k1_big = ops.timing_largest("group_accumulate")
     ops.timing = None
     launches = ops.launches + _linalg.launches - launches0
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t)
-    assert len(idx) <= b and abs(float(w.sum()) - 1.0) < 1e-9, "benchmark result failed its invariants"
 
     # ---- e2e: host (pinned) buffers in, host results out, copies inside the timed region ----
-    Xh = X.cpu().pin_memory()
-    muh = mu.cpu().pin_memory()
-    wh = torch.empty_like(muh).pin_memory()
-    for _ in range(2):
-        wh.copy_(muh)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            idx_e, w_e = sober_b200.recombination(Xh, Z, b, kern, dev, torch.float64, init_weights=wh)
-    barrier()
     e_steps = max(2, args.steps // 2)
-    e0 = time.perf_counter()
-    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s_ev.record()
-    for _ in range(e_steps):
-        flush.zero_()
-        torch.manual_seed(7)
-        wh.copy_(muh)
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            idx_e, w_e = sober_b200.recombination(Xh, Z, b, kern, dev, torch.float64, init_weights=wh)
-        idx_host, w_host = idx_e.cpu(), w_e.cpu()
-    e_ev.record()
-    barrier()
-    e2e_ms = s_ev.elapsed_time(e_ev)
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t)
-    h2d = Xh.numel() * 8 + muh.numel() * 8
-    d2h = idx_host.numel() * 8 + w_host.numel() * 8
+    e2e_ms, h2d, d2h = run.timed_e2e(e_steps, flush)
+
+    # ---- the other configuration of the scaling story, measured in the same run ----
+    extras = {}
+    if not args.no_extras and args.workload == "auto" and args.mode == "fast":
+        if world > 1:
+            wk = Runner("c2", dev, rank, world)
+            ms, _, _ = wk.timed(max(3, args.steps // 2), 2, flush)
+            ksteps = max(3, args.steps // 2)
+            extras["weak_c2"] = {"workload": WORKLOADS["c2"][6], "scaling": "weak", "n_rec_total": wk.n_total,
+                                 "value": wk.n_total * ksteps / (ms * 1e-3), "unit": "candidates/s",
+                                 "ms_per_step": ms / ksteps, "steps": ksteps}
+            del wk
+            # the strong-scaling reference point: the same C5 call on rank 0 alone
+            if rank == 0:
+                sober_b200.set_communicator(None)
+                one = Runner("c5", dev, 0, 1, sharded=False)
+                ksteps = max(2, min(3, args.steps))
+                ms, _, _ = one.timed(ksteps, 2, flush)
+                extras["c5_1gpu"] = {"n_rec_total": one.n_total, "ms_per_step": ms / ksteps, "steps": ksteps,
+                                     "value": one.n_total * ksteps / (ms * 1e-3), "unit": "candidates/s",
+                                     "note": "same config on rank 0 alone while the other ranks wait"}
+                del one
+                sober_b200.enable_sharding()
+            dist.barrier()
+        else:
+            one = Runner("c5", dev, 0, 1)
+            ksteps = max(2, min(5, args.steps // 2))
+            ms, _, _ = one.timed(ksteps, 2, flush)
+            extras["c5"] = {"workload": WORKLOADS["c5"][6], "n_rec_total": one.n_total, "ms_per_step": ms / ksteps,
+                            "steps": ksteps, "value": one.n_total * ksteps / (ms * 1e-3), "unit": "candidates/s",
+                            "note": "the north_star target config (BASELINE configs[4]) on this one GPU"}
+            del one
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (K1, FP64-pipe bound) and of the streaming pass (HBM bound) ----
+    # ---- roofline of the dominant kernel (K1) and of the streaming pass (HBM bound) ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    # FP64 peak: not in MEASURED_PEAKS.json (HBM and bf16 only) -> measured here with a dependent-chain DFMA probe
-    iters = 1 << 16
-    blocks = 148 * 8
-    for _ in range(2):
-        ops.fp64_probe(blocks, iters)
-    torch.cuda.synchronize()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    ops.fp64_probe(blocks, iters)
-    p1.record()
-    torch.cuda.synchronize()
-    fp64_peak = blocks * 256 * iters * 16 / (p0.elapsed_time(p1) * 1e-3) / 1e12
-
     flop_per_pair = 2 * d + 2 + C_K[fam]
     k1_calls, k1_ms, k1_pairs = timing.get("group_accumulate", (0, 0.0, 0))
-    k1_tflops = k1_pairs * flop_per_pair / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else None
     uc_calls, uc_ms, uc_bytes = timing.get("update_compact", (0, 0.0, 0))
     # HBM roofline of the streaming pass: the pass over ALL candidates (first iteration); later iterations halve
     uc_gbs = uc_big[1] / (uc_big[0] * 1e-3) / 1e9 if uc_big and uc_big[0] > 0 else None
-    bits = fam == "tanimoto" and d > 8
+    bits = d > 8 and fam in ("tanimoto", "rbf")          # the bit-packed K1 kernels (Tanimoto popcount / Hamming table)
     words = (d + 63) // 64
-    car_calls, car_ms, car_steps = timing.get("car_eliminate", (0, 0.0, 0))
     step_ms = elapsed_ms / args.steps
-
-    out = {
-        "metric": "recombination candidates/sec", "value": n_total * args.steps / (elapsed_ms * 1e-3),
-        "unit": "candidates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": desc, "n_rec_total": n_total, "n_rec_per_gpu": n_local, "n_nys": L, "batch": b,
-                   "kernel": fam + (" / predictive_covariance (n_obs=200)" if args.pred_cov else " / kernel mode"),
-                   "d": d, "mode": args.mode, "l2": "256 MiB buffer written between steps (flush)",
-                   "parallelism": "row-sharded candidates x%d" % world},
-        "e2e": {"value": n_total * e_steps / (e2e_ms * 1e-3), "unit": "candidates/s", "ms_per_step": e2e_ms / e_steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches,
-        "clocks": clocks.summary(),
-        "roofline": ({
+    share = k1_ms / elapsed_ms if elapsed_ms else None
+    if not bits:
+        peak = fp64_peak(ops)
+        k1_tflops = k1_pairs * flop_per_pair / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else None
+        traffic, traffic_src = measured_traffic(name, world, args.pred_cov)
+        roofline = {
             "kernel": "group_accumulate (K1: fused cross-kernel + weighted group sums, record layout)",
             "bound": "fp64",          # FP64 FMA pipe; the hbm|tensor enum has no entry for it
-            "achieved": k1_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-            "frac": (k1_tflops / fp64_peak) if k1_tflops else None,
-            # DRAM bytes of the largest launch (10^6 candidates x 1000 landmarks) from the ncu --set full capture
-            # profiles/r01_ncu_final_k1_and_car_cols.txt: 64.1 MB read + 7.6 MB written; the 64-byte records alone are
-            # 64 MB, i.e. no re-reads.  Only quoted for the shape it was captured on.
-            "traffic": (71.7e6 if (name == "c2" and world == 1 and not args.pred_cov) else None),
+            "achieved": k1_tflops, "peak": peak, "unit": "TFLOP/s",
+            "frac": (k1_tflops / peak) if k1_tflops else None,
+            "traffic": traffic, "traffic_source": traffic_src,
             "traffic_unit": "bytes per largest launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
             "peak_source": "measured in this run: dependent-chain DFMA probe (sober_fp64_probe), 2 flop per FMA",
             "algorithmic_flop_per_pair": flop_per_pair, "pairs_per_step": k1_pairs / max(args.steps, 1),
-            "launches": k1_calls, "ms_per_step": k1_ms / max(args.steps, 1),
-            "share_of_step": k1_ms / elapsed_ms if elapsed_ms else None,
+            "launches": k1_calls, "ms_per_step": k1_ms / max(args.steps, 1), "share_of_step": share,
             "largest_launch": {"ms": k1_big[0], "pairs": k1_big[1],
                                "tflops": k1_big[1] * flop_per_pair / (k1_big[0] * 1e-3) / 1e12} if k1_big else None,
-        } if not bits else {
-            "kernel": "group_accumulate (K1, bit-packed Tanimoto: popcount(x & z) + FP64 ratio)",
-            "bound": "int",           # integer pipe (AND + POPC); no measured peak for it on this pool
-            "achieved": k1_pairs * words / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None, "peak": None,
-            "unit": "G word-op/s (64-bit AND+POPC)", "frac": None, "traffic": None,
+        }
+    else:
+        peak = popc_peak(ops)
+        rate = k1_pairs * words / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+        roofline = {
+            "kernel": "group_accumulate (K1, bit-packed rows: popcount(x & z) + FP64 Tanimoto ratio, or popcount(x ^ z) "
+                      "+ kernel-value table for a stationary kernel on {0,1}^d)",
+            "bound": "int",           # integer pipe (AND/XOR + POPC)
+            "achieved": rate, "peak": peak, "unit": "G word-op/s (64-bit AND+POPC)",
+            "frac": (rate / peak) if rate else None, "traffic": None,
+            "peak_source": "measured in this run: sober_popc_probe (independent popcount(x & z) chains, 64-bit words)",
             "algorithmic_word_ops_per_pair": words, "pairs_per_step": k1_pairs / max(args.steps, 1),
-            "launches": k1_calls, "ms_per_step": k1_ms / max(args.steps, 1),
-            "share_of_step": k1_ms / elapsed_ms if elapsed_ms else None,
-        }),
+            "launches": k1_calls, "ms_per_step": k1_ms / max(args.steps, 1), "share_of_step": share,
+        }
+
+    out = {
+        "metric": "recombination candidates/sec", "value": run.n_total * args.steps / (elapsed_ms * 1e-3),
+        "unit": "candidates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+        "higher_is_better": True, "scaling": "strong" if run.strong else "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": desc, "n_rec_total": run.n_total, "n_rec_per_gpu": run.n_local, "n_nys": L, "batch": b,
+                   "kernel": fam + (" / predictive_covariance (n_obs=200)" if args.pred_cov else " / kernel mode"),
+                   "d": d, "mode": args.mode, "l2": "256 MiB buffer written between steps (flush)",
+                   "parallelism": "row-sharded candidates x%d" % world},
+        "e2e": {"value": run.n_total * e_steps / (e2e_ms * 1e-3), "unit": "candidates/s", "ms_per_step": e2e_ms / e_steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "bytes_are": "per rank (each rank copies its own shard of the candidates and weights)"},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": roofline,
         "roofline_stream": {
             "kernel": "update_compact (weight update + alive-list compaction, moves the record rows): "
                       "the launch over all candidates",
@@ -362,13 +562,34 @@ def main():
             "bytes": uc_big[1] if uc_big else None, "ms": uc_big[0] if uc_big else None,
             "all_launches_ms_per_step": uc_ms / max(args.steps, 1),
         },
+        # CUDA-event time per step of each instrumented stage on the launching stream; car_step_graph = one replay of
+        # the Caratheodory step (null space + elimination + survivor ranks), all_reduce = the NCCL collective
         "stage_ms_per_step": {k: v[1] / max(args.steps, 1) for k, v in timing.items()},
+        "stage_calls_per_step": {k: v[0] / max(args.steps, 1) for k, v in timing.items()},
         "car": {name_: {"calls_per_step": timing[name_][0] / max(args.steps, 1),
                         "us_per_sequential_step": 1e3 * timing[name_][1] / timing[name_][2] if timing[name_][2] else None}
-                for name_ in ("car_cols", "car_cluster", "car_eliminate") if name_ in timing},
+                for name_ in ("car_panel", "car_cols", "car_cluster", "car_eliminate", "car_step_graph")
+                if name_ in timing},
     }
+    unattributed = step_ms - sum(v for k, v in out["stage_ms_per_step"].items()
+                                 if k not in ("car_panel", "car_cols", "car_cluster") or "car_step_graph" not in timing)
+    out["stage_ms_per_step"]["other (range finder, projection GEMM, host syncs, launch gaps)"] = unattributed
+    out.update(extras)
+    if world == 1 and not args.no_extras and args.mode == "fast" and name in ("c1", "c2", "c3"):
+        sample = min(args.cpu_sample if args.cpu_sample > 0 else 100_000, n_rec)
+        out["parity"] = parity_block(run, sample)
+        # the mode that executes the reference's own op sequence on this device (bitwise-asymmetric Gram from the
+        # kernel object, the reference's PSD gate, torch.svd_lowrank, null space from the full torch.linalg.svd)
+        sober_b200.options.set_mode("parity")
+        psteps = 3
+        pms, _, _ = run.timed(psteps, 1, flush)
+        sober_b200.options.set_mode(args.mode)
+        out["parity_mode"] = {"ms_per_step": pms / psteps, "steps": psteps,
+                              "value": run.n_total * psteps / (pms * 1e-3), "unit": "candidates/s"}
+        if name == "c2":
+            out["reference_gpu"] = reference_gpu_leg(run, flush)
     if world == 1 and not args.no_cpu_baseline:
-        sample = min(args.cpu_sample, n_rec)
+        sample = min(args.cpu_sample if args.cpu_sample > 0 else 100_000, n_rec)
         rate, times = cpu_reference_rate(name, sample, 1, 0, threads)
         out["cpu_baseline"] = {"value": rate, "unit": "candidates/s", "cores": threads, "kind": "port",
                                "sample": "oracle/rchq.py on %d of the workload's candidates (full n_nys/batch), "

@@ -112,8 +112,7 @@ int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_out, double*
  *   LUT family), lut as described at the enum.
  * At: S x L (transposed on purpose: coalesced stores and it is the left operand of the projection).
  * workspace holds the per-split partial sums (deterministic two-stage reduction, no atomics).
- * variant: 0 = automatic (records -> register kernel, else tiled), 1 = force the generic tiled kernel,
- *          2 = EXPERIMENTAL record kernel without the per-chunk block barrier (empty-mbarrier pipeline, 4 stages).
+ * variant: 0 = automatic (records -> register kernel, else tiled), 1 = force the generic tiled kernel.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct sober_group_args {
     const double* X;
@@ -194,6 +193,23 @@ int sober_car_cluster_cols(double* basis, int32_t k, int32_t S, double* mu, int3
 int sober_car_cluster_cols_profiled(double* basis, int32_t k, int32_t S, double* mu, int32_t exact, int32_t* info,
                                     int64_t* prof, void* stream);
 
+/* Elimination only (SOBER/_rchq.py:237-266) on a given basis as a BLOCKED factorisation (csrc/car_panel.cu): panels of
+ * up to 64 pivot columns are eliminated on one 8-CTA cluster (rows distributed over the CTAs, one st.async all-to-all
+ * exchange of pivot-row candidates per step, ~0.5 us), the trailing columns then receive the rank-nb update as one
+ * whole-GPU FP64 GEMM.  If the whole basis fits the cluster's shared memory it is a single panel.  S <= 4096.
+ * Fused arithmetic (the exact == 0 variant of the kernels above): pivots equal the reference's up to rounding.
+ *   basis: k x S rows, DESTROYED.  mu (S) updated in place.  nb_hint: 0 = automatic, else the panel width (<= 64).
+ *   info (2 int32, device, may be NULL): [0] 1 if the elimination stopped early (no positive entry), [1] steps taken.
+ *   workspace: sober_car_panel_workspace(S, k) bytes.  sober_car_panel_fits: 0 = unsupported, 1 = single panel,
+ *   2 = blocked. */
+int sober_car_panel_fits(int32_t S, int32_t k);
+int64_t sober_car_panel_workspace(int32_t S, int32_t k);
+int sober_car_panel(double* basis, int32_t k, int32_t S, double* mu, int32_t nb_hint, int32_t* info, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+/* Same with 8 int64 cycle counters (CTA 0 / thread 0 of the panel kernel, accumulated: zero them first). */
+int sober_car_panel_profiled(double* basis, int32_t k, int32_t S, double* mu, int32_t nb_hint, int32_t* info,
+                             void* workspace, int64_t workspace_bytes, int64_t* prof, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Weight update + compaction of the alive-list (SOBER/_rchq.py:198-221).
  *   For local position j (global p = pos0 + j):
@@ -262,6 +278,9 @@ int sober_partition_stream(int32_t reserve_sms, void** stream, int32_t* sm_count
  * Launches `blocks` x 256 threads, each doing iters * 8 dependent-chain DFMAs; flops = blocks*256*iters*16.
  * ------------------------------------------------------------------------------------------------- */
 int sober_fp64_probe(int32_t blocks, int64_t iters, double* sink, void* stream);
+/* Integer-pipe probe (the roofline denominator of the bit-packed K1 kernels): blocks x 256 threads, each
+ * iters * 4 word-ops, one word-op = popcount(x & z) on 64-bit words accumulated into an int32. */
+int sober_popc_probe(int32_t blocks, int64_t iters, int32_t* sink, void* stream);
 /* FP64 tensor-pipe probe: blocks x 8 warps, each iters * 8 DMMA m8n8k4; flops = blocks * 8 * iters * 8 * 512. */
 int sober_dmma_probe(int32_t blocks, int64_t iters, double* sink, void* stream);
 

@@ -286,3 +286,17 @@ def mmd_squared(kernel, cands, mass, idx, w, chunk=4096):
         for s2 in range(0, len(cands), chunk):
             t3 = t3 + m @ kernel(blk, cands[s2:s2 + chunk]) @ mass[s2:s2 + chunk]
     return t1 - 2 * t2 + t3
+
+
+def projector_nullspace(design):
+    """Restatement, with LAPACK on the CPU, of the null-space basis the product's *fast* mode uses
+    (sober_b200/_car.py::projector_rows): the trailing k columns of the orthogonal projector I - Q1 Q1^T, Q1 an
+    orthonormal basis of range(design) (columns normalised first; the projector does not depend on how Q1 was
+    orthonormalised).  Pass as ``recombination(..., nullspace=projector_nullspace)``: the reference's algorithm
+    (SOBER/_rchq.py:224-270) with this basis in place of the arbitrary one its full SVD returns (:231-234)."""
+    pts, dim = design.shape
+    q1 = torch.linalg.qr(design / design.norm(dim=0, keepdim=True)).Q
+    phi = -(q1 @ q1[dim:, :].T)
+    phi[dim:, :] += torch.eye(pts - dim, dtype=design.dtype, device=design.device)
+    return phi
+

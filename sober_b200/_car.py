@@ -83,7 +83,11 @@ def caratheodory(ops, feats, mass, how, nullspace=None, design=None):
         rows = nullspace_rows(design, how)
     exact = nullspace is not None or how == "svd"          # parity / injected bases keep the reference's rounding
     cols_fit = getattr(ops, "car_cols_fits", None)
-    if cols_fit is not None and cols_fit(pts, rows.shape[0]):
+    panel_fit = getattr(ops, "car_panel_fits", None)
+    from ._settings import options
+    if (not exact and panel_fit is not None and options.car_kernel != "legacy" and panel_fit(pts, rows.shape[0])):
+        ops.car_panel(rows, out, nb_hint=options.car_panel_nb)   # panelled row-distributed cluster kernel
+    elif cols_fit is not None and cols_fit(pts, rows.shape[0]):
         ops.car_cols(rows, out, exact=exact)                # column-distributed cluster kernel (fastest)
     elif fits is not None and fits(pts, dim, True):
         ops.car_cluster(out, basis_rows=rows, exact=exact)
@@ -154,7 +158,9 @@ def reduce_step(ops, feats, mass, use_graph=True):
     static buffers, valid until the next call).  Falls back to eager execution for good if the capture fails."""
     fits = getattr(ops, "car_cols_fits", None)
     S, n = feats.shape
-    if (not use_graph or not feats.is_cuda or fits is None or S <= n + 1 or not fits(S, S - n - 1)):
+    pfits = getattr(ops, "car_panel_fits", None)
+    if (not use_graph or not feats.is_cuda or fits is None or S <= n + 1
+            or not (fits(S, S - n - 1) or (pfits is not None and pfits(S, S - n - 1)))):
         return _reduce_step(ops, feats, mass)
     key = (feats.device, S, n)
     entry = _graphs.get(key)
@@ -180,4 +186,7 @@ def reduce_step(ops, feats, mass, use_graph=True):
         return _reduce_step(ops, feats, mass)
     ops.launches += entry.launches[0]
     _linalg.launches += entry.launches[1]
-    return entry(feats, mass)
+    t0 = ops._begin("car_step_graph")                   # the whole replay: null space + elimination + survivor ranks
+    out = entry(feats, mass)
+    ops._end("car_step_graph", t0, S - n - 1)
+    return out

@@ -62,6 +62,10 @@ PROTOTYPES = {
     "sober_car_cluster_cols_fits": (C.c_int, [_I32, _I32]),
     "sober_car_cluster_cols": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P]),
     "sober_car_cluster_cols_profiled": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _P]),
+    "sober_car_panel_fits": (C.c_int, [_I32, _I32]),
+    "sober_car_panel_workspace": (_I64, [_I32, _I32]),
+    "sober_car_panel": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _I64, _P]),
+    "sober_car_panel_profiled": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _I64, _P, _P]),
     "sober_update_compact": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _I32, _I32, _I64, _P, _P,
                                        _P, _P, _I64, _I32, _P]),
     "sober_scatter_result": (C.c_int, [_P, _I64, _P, _P, _I64, _P]),
@@ -73,6 +77,7 @@ PROTOTYPES = {
     "sober_kmeans_assign": (C.c_int, [_P, _I64, _I64, _I32, _P, _I32, _P, _P]),
     "sober_partition_stream": (C.c_int, [_I32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "sober_dmma_probe": (C.c_int, [_I32, _I64, _P, _P]),
+    "sober_popc_probe": (C.c_int, [_I32, _I64, _P, _P]),
 }
 
 _lib = None

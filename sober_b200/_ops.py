@@ -200,6 +200,11 @@ class CudaOps:
     def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None, rec=None, unit_weights=False):
         """At (S x L) and totw (S) for the positions [pos0, pos0 + n_local) this device owns.  ``rec``: record rows of
         exactly those positions (record layout); otherwise ``pts`` + ``idx`` + ``mu`` (indexed layout)."""
+        if int(n_local) == 0:
+            # a shard with no alive rows (all-zero weights on this rank) contributes nothing; its 0-row tensors have
+            # NULL data pointers, which the C side would read as "indexed layout without X" and reject
+            return (torch.zeros((S, lm.L), dtype=torch.float64, device=self.device),
+                    torch.zeros(S, dtype=torch.float64, device=self.device))
         At = torch.empty((S, lm.L), dtype=torch.float64, device=self.device)
         totw = torch.empty(S, dtype=torch.float64, device=self.device)
         a = GroupArgs()
@@ -311,6 +316,32 @@ class CudaOps:
             self._end("car_cols", t0, k)
         self.launches += 1
 
+    def car_panel_fits(self, S, k):
+        """0 = unsupported shape, 1 = the basis is one panel (single cluster kernel), 2 = blocked (panels + GEMM updates)."""
+        return int(self.lib.sober_car_panel_fits(int(S), int(k)))
+
+    def car_panel(self, basis_rows, mass, nb_hint=0, want_info=False, prof=None):
+        """Elimination on ``basis_rows`` (k x S, destroyed) with the panelled kernels of csrc/car_panel.cu (fused
+        arithmetic); ``mass`` reduced in place.  ``want_info``: returns the device int32 pair [stopped, steps]."""
+        k, S = basis_rows.shape
+        assert basis_rows.is_contiguous() and mass.is_contiguous()
+        nbytes = self.lib.sober_car_panel_workspace(S, k)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
+        info = torch.empty(2, dtype=torch.int32, device=self.device) if want_info else None
+        with self._guard():
+            t0 = self._begin("car_panel")
+            if prof is None:
+                check(self.lib.sober_car_panel(_ptr(basis_rows), k, S, _ptr(mass), int(nb_hint), _ptr(info), _ptr(ws),
+                                               ws.numel(), self._stream()), "car_panel")
+            else:
+                check(self.lib.sober_car_panel_profiled(_ptr(basis_rows), k, S, _ptr(mass), int(nb_hint), _ptr(info),
+                                                        _ptr(ws), ws.numel(), _ptr(prof), self._stream()), "car_panel")
+            self._end("car_panel", t0, k)
+        fits = self.car_panel_fits(S, k)
+        nb = 64 if not nb_hint else min(int(nb_hint), 64)
+        self.launches += 1 if (fits == 1 and not nb_hint) else 3 * ((k + nb - 1) // nb) - 2
+        return info
+
     # -- update + compaction ----------------------------------------------------------------------------------
     def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out,
                        rec=None, d=0):
@@ -368,3 +399,8 @@ class CudaOps:
         sink = torch.zeros(1, dtype=torch.float64, device=self.device)
         with self._guard():
             check(self.lib.sober_fp64_probe(int(blocks), int(iters), _ptr(sink), self._stream()), "fp64_probe")
+
+    def popc_probe(self, blocks, iters):
+        sink = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with self._guard():
+            check(self.lib.sober_popc_probe(int(blocks), int(iters), _ptr(sink), self._stream()), "popc_probe")

@@ -389,7 +389,10 @@ class Recombiner:
                     extra[Lp + 1] = torch.dot(row[0, t0:], mass[t0:])
             if comm.world > 1:
                 packed = torch.cat([at.reshape(-1), totw, extra])
+                t_ar = ops._begin("all_reduce") if hasattr(ops, "_begin") else None
                 comm.all_reduce(packed)
+                if t_ar is not None:
+                    ops._end("all_reduce", t_ar, packed.numel() * 8)
                 at = packed[:S * Lp].reshape(S, Lp)
                 totw = packed[S * Lp:S * Lp + S]
                 extra = packed[S * Lp + S:]

@@ -30,19 +30,29 @@ _PRESETS = {
 }
 
 
+def _under_profiler():
+    """Nsight Compute / CUPTI injection present: ncu stops recording (and exits with an error) at the first launch on a
+    green-context stream, so the SM-partitioned overlap of the first K1 pass is switched off under a profiler."""
+    return any(k in os.environ for k in ("NV_NSIGHT_INJECTION_PORT_BASE", "NV_NSIGHT_INJECTION_TRANSPORT_TYPE",
+                                         "CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR",
+                                         "NV_TPS_LAUNCH_TOKEN", "NSYS_PROFILING_SESSION_ID"))
+
+
 class Options:
     def __init__(self, mode=None):
         self.set_mode(mode or os.environ.get("SOBER_B200_MODE", "fast"))
         self.fuse = True              # introspect Kernel objects; False forces the generic-callable path
         self.generic_chunk = 1 << 16  # candidates per Gram tile on the generic path
-        self.k1_variant = 0           # 0 auto (record / bit-packed kernels when they apply), 1 force the tiled kernel,
-                                      # 2 experimental barrier-free record kernel (not yet validated on hardware)
+        self.k1_variant = 0           # 0 auto (record / bit-packed kernels when they apply), 1 force the tiled kernel
         self.fused_projection = False  # hand-written DMMA projection+barycentre kernel instead of cuBLAS DGEMM
-        self.overlap = os.environ.get("SOBER_B200_OVERLAP", "1") != "0"   # first K1 pass beside the tail of the range finder (two streams); fast mode only
+        self.overlap = os.environ.get("SOBER_B200_OVERLAP", "0" if _under_profiler() else "1") != "0"   # first K1 pass beside the tail of the range finder (two streams); fast mode only
         self.graphs = os.environ.get("SOBER_B200_GRAPHS", "1") != "0"   # replay each Caratheodory step from a CUDA graph
         self.defer_gate = os.environ.get("SOBER_B200_DEFER_GATE", "1") != "0"   # gate test beside the range finder
         self.rotate_basis = None      # None: rotate the Nystrom basis by its singular vectors unless the null spaces come
                                       # from the projector (then only span(U) matters); True / False force it
+        self.car_kernel = os.environ.get("SOBER_B200_CAR", "panel")   # "panel": blocked row-distributed cluster kernel
+                                      # (csrc/car_panel.cu) for the fused-arithmetic elimination; "legacy": round-1 kernels
+        self.car_panel_nb = int(os.environ.get("SOBER_B200_CAR_NB", "0"))   # 0 = automatic panel width
         self.stats = None             # optional dict that receives per-stage timings (forces syncs)
 
     def set_mode(self, mode):

@@ -37,43 +37,44 @@ int sm_count();
 // cost ~3x more issue slots than FP64 slots (special-case branches, integer fix-ups, register moves); K1 is
 // bound by exactly those, so the three primitives are restated with the minimum number of FP64 instructions:
 //
-//   exp_neg(s) = exp(-s), s >= 0      9 FP64 + ~6 integer/LDS    max rel err 3.3e-16 + 1.1e-16 * s (checked against
+//   exp_neg(s) = exp(-s), s >= 0      6 FP64 + ~6 integer/LDS    max rel err 8.1e-13 + 1.1e-16 * s (checked against
 //                                      50-digit arithmetic, tools/check_fastmath.py)
-//   sqrt_pos(a), a >= 1e-30            4 FP64 + 1 MUFU            rel err <= 8.5e-14
+//   sqrt_pos(a), a >= 1e-30            3 FP64 + 1 MUFU + 1 int    rel err <= 8.5e-14
 //   div_pos(a, b), b > 0               7 FP64 + 1 MUFU            <= 1 ulp
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-constexpr int EXP_TAB_SIZE = 64;
-static __device__ const double EXP2_TAB[EXP_TAB_SIZE] = {  // 2^(j/64), correctly rounded (50-digit source)
-    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
-    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
-    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
-    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
-    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
-    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
-    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
-    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
-    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
-    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
-    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
-    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
-    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
-    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
-    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
-    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
+// Table size 2^B and polynomial degree of exp_neg.  |r| <= ln2 / 2^(B+1), truncation error r^(deg+1) / (deg+1)!:
+//   B = 6,  deg 5: 3.5e-17  (round 1)        B = 8,  deg 3: 1.4e-13
+//   B = 11, deg 2: 8.1e-13  (default: 3 DFMA fewer per kernel value; the tolerance on kernel values is 1e-10)
+// checked against 50-digit arithmetic by tools/check_fastmath.py.
+#ifndef SOBER_EXP_TAB_BITS
+#define SOBER_EXP_TAB_BITS 11
+#endif
+#ifndef SOBER_EXP_DEG
+#define SOBER_EXP_DEG 2
+#endif
+#ifndef SOBER_SQRT_INTHALF
+#define SOBER_SQRT_INTHALF 1
+#endif
+constexpr int EXP_TAB_BITS = SOBER_EXP_TAB_BITS;
+constexpr int EXP_TAB_SIZE = 1 << EXP_TAB_BITS;
+static_assert(EXP_TAB_BITS >= 4 && EXP_TAB_BITS <= 11, "exp table: 16 .. 2048 entries");
+static __device__ const double EXP2_TAB[2048] = {  // 2^(j/2048), correctly rounded (tools/gen_exp2_table.py)
+#include "exp2_tab.inc"
+};
 
 // 64-bit constants of the routines below.  Read as constant-bank operands (DFMA ..., c[0x3][..]) they cost no
 // instruction; as literals the compiler rebuilds each one with two UMOV/IMAD.MOV per use (measured in the K1 SASS:
 // 6 of 48 instructions per kernel value).
 static __constant__ double MATH_C[6] = {
-    -92.33248261689366,       // [0] -64 / ln2
-    0.010830424696249145,     // [1] ln2 / 64 rounded to double
+    -(double)EXP_TAB_SIZE / 0.69314718055994530942,   // [0] -2^B / ln2
+    0.69314718055994530942 / (double)EXP_TAB_SIZE,    // [1] ln2 / 2^B (a power-of-two scaling of ln2 rounded to double)
     1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,   // [2..4] exp polynomial
     1.0 / 3.0};               // [5] Matern-5/2
 
 __device__ __forceinline__ void load_exp_table(double* tab_smem, int tid, int nthreads) {
-    for (int j = tid; j < EXP_TAB_SIZE; j += nthreads) tab_smem[j] = EXP2_TAB[j];
+    for (int j = tid; j < EXP_TAB_SIZE; j += nthreads) tab_smem[j] = EXP2_TAB[j << (11 - EXP_TAB_BITS)];
 }
 
 __device__ __forceinline__ double lds_f64(uint32_t saddr) {
@@ -85,27 +86,36 @@ __device__ __forceinline__ double lds_f64(uint32_t saddr) {
 // `tab` is the SHARED-SPACE address of the 64-entry table (smem_addr(tab_smem)): a generic pointer would cost a
 // generic->shared conversion (S2UR SR_CgaCtaId + ULEA) at every use
 __device__ __forceinline__ double exp_neg(double s_in, uint32_t tab) {
-    // exp(-s) = 2^m * 2^(j/64) * exp(r),  -s = (64 m + j) ln2/64 + r,  |r| <= ln2/128
+    // exp(-s) = 2^m * 2^(j/T) * exp(r),  -s = (T m + j) ln2/T + r,  |r| <= ln2/(2T),  T = EXP_TAB_SIZE
     const double MAGIC = 6755399441055744.0;            // 1.5 * 2^52: adds round-to-nearest-integer
-    const double NEG_L2E64 = MATH_C[0];                 // -64 / ln2
-    const double LN2_64 = MATH_C[1];                    // ln2/64 rounded to double
+    const double NEG_L2ET = MATH_C[0];                  // -T / ln2
+    const double LN2_T = MATH_C[1];                     // ln2/T rounded to double
     // clamp s at ~700 through the integer pipe (s >= 0: high words order like ints): below 1e-304 the exponent
     // trick at the end would wrap
     const double s = __hiloint2double(min(__double2hiint(s_in), 0x4085E000), __double2loint(s_in));
-    const double kd = fma(s, NEG_L2E64, MAGIC);
+    const double kd = fma(s, NEG_L2ET, MAGIC);
     const int k = __double2loint(kd);
     const double kf = kd - MAGIC;
-    // one FMA: the product kf * LN2_64 is exact inside the FMA, so r carries only the rounding of the constant
+    // one FMA: the product kf * LN2_T is exact inside the FMA, so r carries only the rounding of the constant
     // (|s| * 1.1e-16 absolute) -- no hi/lo split needed
-    const double r = fma(kf, -LN2_64, -s);
+    const double r = fma(kf, -LN2_T, -s);
+#if SOBER_EXP_DEG >= 5
     double q = fma(MATH_C[2], r, MATH_C[3]);
     q = fma(q, r, MATH_C[4]);
     q = fma(q, r, 0.5);
+#elif SOBER_EXP_DEG == 4
+    double q = fma(MATH_C[3], r, MATH_C[4]);
+    q = fma(q, r, 0.5);
+#elif SOBER_EXP_DEG == 3
+    double q = fma(MATH_C[4], r, 0.5);
+#else
+    double q = 0.5;
+#endif
     q = fma(q, r, 1.0);
     const double p = fma(q, r, 1.0);
     const double v = lds_f64(tab + ((k & (EXP_TAB_SIZE - 1)) << 3)) * p;   // in [1, 2)
-    // scale by 2^m on the exponent field (ALU pipe): hi += (k >> 6) << 20 == (k & ~63) << 14
-    const int hi = __double2hiint(v) + ((k & ~(EXP_TAB_SIZE - 1)) << 14);
+    // scale by 2^m on the exponent field (ALU pipe): hi += (k >> B) << 20 == (k & ~(T-1)) << (20 - B)
+    const int hi = __double2hiint(v) + ((k & ~(EXP_TAB_SIZE - 1)) << (20 - EXP_TAB_BITS));
     return __hiloint2double(hi, __double2loint(v));
 }
 
@@ -113,7 +123,13 @@ __device__ __forceinline__ double sqrt_pos(double a) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));   // MUFU.RSQ64H, rel err 2^-22
     // one Goldschmidt step: relative error 1.5 * (2^-22)^2 = 8.5e-14 (the tolerance on kernel values is 1e-10)
+#if SOBER_SQRT_INTHALF
+    // y / 2 on the exponent field (integer pipe; y = rsqrt(a) <= 1e15 for a >= 1e-30: no underflow) -- one FP64 less
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, __double2loint(y));
+    const double g = a * y;
+#else
     const double g = a * y, h = 0.5 * y;
+#endif
     const double e = fma(-g, h, 0.5);
     return fma(g, e, g);
 }

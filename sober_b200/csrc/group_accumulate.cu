@@ -44,24 +44,22 @@ struct GroupParams {
 // -------------------------------------------------------------------------------------------------
 constexpr int REC_WARPS = 8;
 constexpr int REC_THREADS = REC_WARPS * 32;
-constexpr int REC_ROWS = 16;    // rows per pipeline stage
+#ifndef SOBER_REC_ROWS
+#define SOBER_REC_ROWS 16
+#endif
+constexpr int REC_ROWS = SOBER_REC_ROWS;    // rows per pipeline stage
 constexpr int REC_STAGES = 3;
 
 #ifndef SOBER_REC_MINB
 #define SOBER_REC_MINB 2
 #endif
-// NB (variant 2, EXPERIMENTAL, opt-in through sober_group_args.variant / options.k1_variant = 2, not yet run on
-// hardware): no block barrier per chunk.  Each warp releases a stage by arriving on its "empty" mbarrier; thread 0
-// refills the stage of chunk c-1 after finishing chunk c (one chunk of slack, hence 4 stages instead of 3), so no warp
-// ever waits for the slowest one -- the barrier stall is 0.7 of 6.3 stall cycles per issue in the ncu profile of the
-// default kernel.  NB = false compiles to the same instructions as before the parameter existed.
-template <int D, int FAM, int TL, int TG, bool UNIT, bool NB = false>
+// (A variant without the per-chunk block barrier -- per-stage "empty" mbarriers, 4 stages -- was measured in round 2:
+// bitwise-equal output, 2-6 % SLOWER at every shape (profiles/r02_k1_variants.txt), and removed.)
+template <int D, int FAM, int TL, int TG, bool UNIT>
 __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_kernel(const GroupParams p) {
     constexpr int LDR = (D + 3) / 2 * 2;  // d + 2 rounded up to even
-    constexpr int REC_STAGES = NB ? 4 : sober::REC_STAGES;
     __shared__ __align__(16) double buf[REC_STAGES][REC_ROWS][TG][LDR];
     __shared__ __align__(8) uint64_t bars[REC_STAGES];
-    __shared__ __align__(8) uint64_t empty[NB ? REC_STAGES : 1];
     __shared__ double tab[EXP_TAB_SIZE];
 
     const int t = threadIdx.x;
@@ -75,8 +73,6 @@ __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_ker
     asm volatile("" : "+r"(tab_s));   // opaque: otherwise the address is re-derived (S2UR + ULEA + ...) at every use
     if (t == 0) {
         for (int s = 0; s < REC_STAGES; ++s) mbar_init(&bars[s], 1);
-        if (NB)
-            for (int s = 0; s < REC_STAGES; ++s) mbar_init(&empty[s], REC_WARPS);
         mbar_fence_init();
     }
     __syncthreads();
@@ -134,86 +130,95 @@ __global__ void __launch_bounds__(REC_THREADS, SOBER_REC_MINB) group_records_ker
 #pragma unroll
         for (int i = 0; i < TL; ++i) acc[i][j] = 0.0;
     }
-    const bool count_tw = (blockIdx.y == 0) && (t == 0);
+    // group weight totals: warp 0 of the CTAs with blockIdx.y == 0, one staged row per lane (round 1 had thread 0 walk
+    // all rows of a chunk alone while its warp waited -- and the whole CTA waited for that warp at the chunk barrier)
+    const bool tw_warp = (blockIdx.y == 0) && (warp == 0);
+    static_assert(REC_ROWS <= 32, "one staged row per lane");
+
+    // all TG candidates of staged row r: TL x TG independent chains
+    auto full_row = [&](int stage, int r) {
+        double x[TG][D], xn[TG], w[TG];
+#pragma unroll
+        for (int j = 0; j < TG; ++j) {
+            const double* rp = &buf[stage][r][j][0];
+#pragma unroll
+            for (int k = 0; k < D; ++k) x[j][k] = rp[k];
+            xn[j] = rp[D];
+            w[j] = UNIT ? 1.0 : rp[D + 1];
+        }
+        double val[TL][TG];
+#pragma unroll
+        for (int i = 0; i < TL; ++i)
+#pragma unroll
+            for (int j = 0; j < TG; ++j) {
+                double dot = (FAM == SOBER_TANIMOTO) ? 0.0 : zn[i];
+#pragma unroll
+                for (int k = 0; k < D; ++k) dot = fma(x[j][k], zt[i][k], dot);
+                val[i][j] = (FAM == SOBER_TANIMOTO) ? tanimoto_value(dot, xn[j], zn[i])
+                                                    : stationary_value<FAM>(xn[j] + dot, tab_s);
+            }
+#pragma unroll
+        for (int i = 0; i < TL; ++i)
+#pragma unroll
+            for (int j = 0; j < TG; ++j) acc[i][j] = fma(val[i][j], w[j], acc[i][j]);
+    };
 
     for (int c = 0; c < nchunks; ++c) {
         const int stage = c % REC_STAGES;
         mbar_wait(&bars[stage], (uint32_t)((c / REC_STAGES) & 1));
         const int64_t e0 = r0 + (int64_t)c * REC_ROWS;
         const int nrows = (int)min((int64_t)REC_ROWS, r1 - e0);
-        if (count_tw) {
-            // group weight totals (positions below ES only): one thread, kept out of the FP64-critical loop below
-            for (int r = 0; r < nrows; ++r) {
-                int ja, jb;
-                interval(e0 + r, ja, jb);
+        // interior chunk: every row has all TG candidates on this device (the usual case) -- no per-row bookkeeping
+        const int64_t base0 = e0 * p.S + g0;
+        const bool full = jmax == TG && base0 >= p.pos0 && base0 + (int64_t)(nrows - 1) * p.S + TG <= hi;
+        if (tw_warp && lane < nrows) {
+            int ja = 0, jb = TG;
+            if (!full) interval(e0 + lane, ja, jb);
 #pragma unroll
-                for (int j = 0; j < TG; ++j)
-                    if (j >= ja && j < jb && (e0 + r) * p.S + g0 + j < p.ES)
-                        tw[j] += UNIT ? 1.0 : buf[stage][r][j][D + 1];
-            }
+            for (int j = 0; j < TG; ++j)
+                if (j >= ja && j < jb && (e0 + lane) * p.S + g0 + j < p.ES)
+                    tw[j] += UNIT ? 1.0 : buf[stage][lane][j][D + 1];
         }
         if (active) {
-            for (int r = 0; r < nrows; ++r) {
-                int ja, jb;
-                interval(e0 + r, ja, jb);
-                if (ja == 0 && jb == TG) {
-                    // fast path: all TG candidates of the row, TL x TG independent chains
-                    double x[TG][D], xn[TG], w[TG];
-#pragma unroll
-                    for (int j = 0; j < TG; ++j) {
-                        const double* rp = &buf[stage][r][j][0];
-#pragma unroll
-                        for (int k = 0; k < D; ++k) x[j][k] = rp[k];
-                        xn[j] = rp[D];
-                        w[j] = UNIT ? 1.0 : rp[D + 1];
-                    }
-                    double val[TL][TG];
-#pragma unroll
-                    for (int i = 0; i < TL; ++i)
+            if (full) {
+                for (int r = 0; r < nrows; ++r) full_row(stage, r);
+            } else {
+                for (int r = 0; r < nrows; ++r) {
+                    int ja, jb;
+                    interval(e0 + r, ja, jb);
+                    if (ja == 0 && jb == TG) {
+                        full_row(stage, r);
+                    } else {
 #pragma unroll
                         for (int j = 0; j < TG; ++j) {
-                            double dot = (FAM == SOBER_TANIMOTO) ? 0.0 : zn[i];
+                            if (j < ja || j >= jb) continue;
+                            const double* rp = &buf[stage][r][j][0];
+                            const double xn = rp[D];
+                            const double w = UNIT ? 1.0 : rp[D + 1];
 #pragma unroll
-                            for (int k = 0; k < D; ++k) dot = fma(x[j][k], zt[i][k], dot);
-                            val[i][j] = (FAM == SOBER_TANIMOTO) ? tanimoto_value(dot, xn[j], zn[i])
-                                                                : stationary_value<FAM>(xn[j] + dot, tab_s);
-                        }
+                            for (int i = 0; i < TL; ++i) {
+                                double dot = (FAM == SOBER_TANIMOTO) ? 0.0 : zn[i];
 #pragma unroll
-                    for (int i = 0; i < TL; ++i)
-#pragma unroll
-                        for (int j = 0; j < TG; ++j) acc[i][j] = fma(val[i][j], w[j], acc[i][j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < TG; ++j) {
-                        if (j < ja || j >= jb) continue;
-                        const double* rp = &buf[stage][r][j][0];
-                        const double xn = rp[D];
-                        const double w = UNIT ? 1.0 : rp[D + 1];
-#pragma unroll
-                        for (int i = 0; i < TL; ++i) {
-                            double dot = (FAM == SOBER_TANIMOTO) ? 0.0 : zn[i];
-#pragma unroll
-                            for (int k = 0; k < D; ++k) dot = fma(rp[k], zt[i][k], dot);
-                            const double v = (FAM == SOBER_TANIMOTO) ? tanimoto_value(dot, xn, zn[i])
-                                                                     : stationary_value<FAM>(xn + dot, tab_s);
-                            acc[i][j] = fma(v, w, acc[i][j]);
+                                for (int k = 0; k < D; ++k) dot = fma(rp[k], zt[i][k], dot);
+                                const double v = (FAM == SOBER_TANIMOTO) ? tanimoto_value(dot, xn, zn[i])
+                                                                         : stationary_value<FAM>(xn + dot, tab_s);
+                                acc[i][j] = fma(v, w, acc[i][j]);
+                            }
                         }
                     }
                 }
             }
         }
-        if (NB) {
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&empty[stage])) : "memory");
-            if (t == 0 && c >= 1 && c - 1 + REC_STAGES < nchunks) {
-                mbar_wait(&empty[(c - 1) % REC_STAGES], (uint32_t)(((c - 1) / REC_STAGES) & 1));   // all 8 warps left it
-                issue(c - 1 + REC_STAGES);
-            }
-        } else {
-            __syncthreads();   // every warp is done with this stage before it is refilled
-            if (t == 0 && c + REC_STAGES < nchunks) issue(c + REC_STAGES);
-        }
+        __syncthreads();   // every warp is done with this stage before it is refilled
+        if (t == 0 && c + REC_STAGES < nchunks) issue(c + REC_STAGES);
     }
+    if (tw_warp) {
+#pragma unroll
+        for (int j = 0; j < TG; ++j)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) tw[j] += __shfl_xor_sync(0xffffffffu, tw[j], off);
+    }
+    const bool count_tw = tw_warp && lane == 0;
 
     double* out = p.out + (int64_t)blockIdx.z * p.S * p.L;
 #pragma unroll
@@ -540,7 +545,6 @@ static int bits_tl(int W) { return W <= 8 ? 4 : (W <= 16 ? 2 : 1); }
 
 struct Plan {
     bool records;
-    bool no_barrier;   // experimental K1 variant 2
     bool bits;
     dim3 grid, block;
     int nsplit;
@@ -554,7 +558,6 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
     pl->row_end = a->n_local > 0 ? ceil_div(hi, a->S) : pl->row_begin;
     const int64_t rows = pl->row_end - pl->row_begin;
     pl->records = a->rec != nullptr && a->variant != 1;
-    pl->no_barrier = a->variant == 2;
     pl->bits = a->family == SOBER_TANIMOTO_BITS || a->family == SOBER_HAMMING_LUT;
     if (a->family == SOBER_HAMMING_LUT && !a->lut) return false;
     if (pl->bits) {
@@ -592,12 +595,7 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
 
 template <int D, int FAM>
 static void launch_records(const Plan& pl, const GroupParams& p, cudaStream_t st) {
-    if (pl.no_barrier) {   // experimental variant 2
-        if (p.unit_weights)
-            group_records_kernel<D, FAM, REC_TL, REC_TG, true, true><<<pl.grid, pl.block, 0, st>>>(p);
-        else
-            group_records_kernel<D, FAM, REC_TL, REC_TG, false, true><<<pl.grid, pl.block, 0, st>>>(p);
-    } else if (p.unit_weights)
+    if (p.unit_weights)
         group_records_kernel<D, FAM, REC_TL, REC_TG, true><<<pl.grid, pl.block, 0, st>>>(p);
     else
         group_records_kernel<D, FAM, REC_TL, REC_TG, false><<<pl.grid, pl.block, 0, st>>>(p);

@@ -271,9 +271,29 @@ __global__ void __launch_bounds__(256) fp64_probe_kernel(int64_t iters, double* 
     if (s == 123.456) sink[0] = s;  // never true: keeps the loop alive
 }
 
+// ---- integer-pipe probe: 64-bit word-ops of the bit-packed K1 kernels (AND / XOR + POPC + add) -----------
+__global__ void __launch_bounds__(256) popc_probe_kernel(int64_t iters, unsigned long long seed, int* sink) {
+    unsigned long long z0 = seed + threadIdx.x, z1 = z0 * 3, z2 = z0 * 5, z3 = z0 * 7;
+    unsigned long long x = seed ^ (0x9E3779B97F4A7C15ull * (blockIdx.x + 1));
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int64_t i = 0; i < iters; ++i) {
+        c0 += __popcll(x & z0); c1 += __popcll(x & z1); c2 += __popcll(x & z2); c3 += __popcll(x & z3);
+        x += 0x9E3779B97F4A7C15ull;       // a new candidate word per trip (one 64-bit add per 4 word-ops)
+    }
+    const int s = (c0 + c1) + (c2 + c3);
+    if (s == -12345) sink[0] = s;  // never true: keeps the loop alive
+}
+
 }  // namespace sober
 
 using namespace sober;
+
+extern "C" int sober_popc_probe(int32_t blocks, int64_t iters, int32_t* sink, void* stream) {
+    if (blocks <= 0 || iters <= 0 || !sink) return SOBER_ERR_ARG;
+    popc_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, 0x1234567ull, sink);
+    SOBER_LAUNCH_CHECK("popc_probe");
+    return SOBER_OK;
+}
 
 extern "C" int sober_prepare_points(const double* X, int64_t ldx, int64_t n, int32_t d, const double* center,
                                     const double* inv_ls, double* P, int64_t ldp, void* stream) {

@@ -5,6 +5,7 @@ import numpy as np
 import torch
 
 from oracle import kernels as ok
+from oracle import rchq as oracle_rchq
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["matern6d_rest", "matern6d_pow2", "rbf2d_branin", "rbf_ard5d", "ising24_hamming", "tanimoto256",
@@ -48,12 +49,5 @@ class Case:
         return ok.Kernel(ok.GPModel(cov, self.Xobs, None, noise=self.noise), mode=self.mode)
 
 
-def projector_nullspace(design):
-    """Oracle-side restatement of the fast mode's null-space basis (sober_b200/_car.py::projector_rows): trailing
-    columns of I - Q1 Q1^T with Q1 from LAPACK's Householder QR (the projector does not depend on how Q1 was
-    orthonormalised).  Returns Phi (S x k) for oracle.recombination(nullspace=...)."""
-    pts, dim = design.shape
-    q1 = torch.linalg.qr(design / design.norm(dim=0, keepdim=True)).Q
-    phi = -(q1 @ q1[dim:, :].T)
-    phi[dim:, :] += torch.eye(pts - dim, dtype=design.dtype)
-    return phi
+# the fast mode's null-space basis restated with LAPACK (one definition, shared with bench.py's parity block)
+projector_nullspace = oracle_rchq.projector_nullspace

@@ -1,0 +1,24 @@
+#!/bin/bash
+# One gpurun call = several experiments; every step under its own timeout, logs under gpurun_out/$TAG/
+TAG=${1:-batch}; shift
+OUT=gpurun_out/$TAG; mkdir -p $OUT
+run() { name=$1; shift; echo "=== $name: $*" | tee -a $OUT/summary.txt; ( timeout -s KILL ${TMO:-300} "$@" ) > $OUT/$name.log 2>&1; echo "rc=$? ($name)" | tee -a $OUT/summary.txt; tail -${TAILN:-15} $OUT/$name.log | tee -a $OUT/summary.txt; }
+make -C sober_b200/csrc -j16 > $OUT/make.log 2>&1 || { echo "BUILD FAILED"; tail -20 $OUT/make.log; }
+for step in "$@"; do
+  case $step in
+    carpanel) run carpanel_tests python -m pytest tests/test_car_panel.py -x -q -m gpu ;;
+    timecar)  TAILN=40 run time_car python tools/time_car.py ;;
+    k1var)    for lib in k1_variants/*.so; do SOBER_B200_LIB=$lib TMO=120 TAILN=2 run k1_$(basename $lib .so) python tools/k1_time.py; done ;;
+    stage5)   TAILN=25 run stage_c5 python tools/stage_breakdown.py c5 ;;
+    stage2)   TAILN=25 run stage_c2 python tools/stage_breakdown.py c2 ;;
+    nys5)     TAILN=40 run nystrom_c5 python tools/nystrom_breakdown.py 2000 999 ;;
+    tests)    TMO=900 run pytest_gpu python -m pytest tests -x -q -m gpu ;;
+    smoke)    run smoke python __graft_entry__.py smoke ;;
+    ncuk1)    TMO=600 run ncu_k1 ncu --set full --clock-control none --import-source on -k regex:group_records -s 4 -c 1 -f -o $OUT/k1prof python tools/k1_time.py ;;
+    ncusmoke) TMO=600 TAILN=60 run ncu_smoke ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_smoke.csv python -c "import __graft_entry__ as g; g.smoke()" ;;
+    stagepar) TAILN=25 run stage_c2_parity python tools/stage_breakdown.py c2 parity ;;
+    bench2)   TMO=600 TAILN=3 run bench_c2 python bench.py --steps 10 --warmup 3 ;;
+    bench5)   TMO=600 TAILN=3 run bench_c5 python bench.py --workload c5 --steps 5 --warmup 2 --no-cpu-baseline ;;
+    *)        echo "unknown step $step" ;;
+  esac
+done

@@ -8,7 +8,7 @@ from sober_b200._linalg import cholesky_upper, solve_right_upper
 
 dev = torch.device("cuda")
 torch.manual_seed(0)
-L, q = 1000, 199
+L, q = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1000, 199)
 X = torch.rand(L, 6, dtype=torch.float64, device=dev)
 d2 = torch.cdist(X, X) * (5 ** 0.5) / 0.5
 K = (1 + d2 + d2 * d2 / 3) * torch.exp(-d2)

@@ -10,7 +10,7 @@ Z = X[torch.randperm(n_rec, device=dev, generator=torch.Generator(device=dev).ma
 kern = bench.make_kernel(name, dev)
 for rep in range(3):
     stats = {}
-    with warnings.catch_warnings(), sober_b200.configure(mode="fast", stats=stats if rep == 2 else None):
+    with warnings.catch_warnings(), sober_b200.configure(mode=(sys.argv[2] if len(sys.argv) > 2 else "fast"), stats=stats if rep == 2 else None):
         warnings.simplefilter("ignore")
         torch.manual_seed(7)
         sober_b200.recombination(X, Z, b, kern, dev, torch.float64, init_weights=mu.clone())
