@@ -117,7 +117,12 @@ __device__ __forceinline__ unsigned long long cp_pack(double ratio, int row) {
 constexpr int CP_B = 8;           // register block: columns of the panel a row thread holds in registers
 constexpr int CP_HB = CP_HDR + CP_B;
 
-template <int RT>
+// Roles inside a CTA:  warp 0 = PIVOT warp (holds all rows of the CTA's block in registers, lane l rows l, l + 32, ...:
+// ratio test, warp-level argmin, the post and the register update never leave the warp -- no block barrier inside a
+// step);  warp 1 = HELPER (follows every exchange: records the multipliers L and the pivots, and -- in the CTA that owns
+// the pivot row -- sends that row's entries right of the block to everybody);  warps 2..7 sleep at the block-end barrier
+// and join for the rank-8 update of the rest of the panel.
+template <int RPL>
 __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanelParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int P = CP_P, B = CP_B, HB = CP_HB;
@@ -125,21 +130,21 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int S = p.S, nb = p.nb, rpcp = p.rpcp, tr = p.tr;
     const int tc = CP_THREADS / tr;
-    const int ri = t & (tr - 1), ci = t / tr;
+    const int ri = t & (tr - 1), ci = t / tr;     // mapping of the block-end update: row ri, columns ci, ci + tc, ...
     const int row0 = r * p.rpc;
     const int nrows = max(0, min(p.rpc, S - row0));
-    const int nwr = tr >> 5;                       // warps of row threads (ci == 0)
-    const bool rowthr = ci == 0;
 
     extern __shared__ __align__(16) double sm[];
     double* panel = sm;                            // [nb][rpcp]   column-major panel (u columns once a block is done)
     double* recv = panel + (size_t)nb * rpcp;      // [2][P][HB]   candidates of the current / next step
     double* gbuf = recv + 2 * P * HB;              // [nb][B]      raw pivot rows of the block, then R (transposed)
     double* lblk = gbuf + (size_t)nb * B;          // [B][B]       in-block multipliers L[q][q']
-    double* stage = lblk + B * B;                  // [2][8][HB]   per step parity and warp: the warp's best row (header + block row)
+    double* stage = lblk + B * B;                  // [HB]         this CTA's candidate (header + block row)
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ __align__(8) uint64_t gbar;
-    __shared__ unsigned long long red_key[2][CP_THREADS / 32];
+    __shared__ int jblk_s[B];
+    __shared__ volatile int helper_read;           // exchanges whose buffer the helper has finished reading
+    __shared__ volatile int stop_s;
 
     if (*(volatile int*)p.state != 0) return;      // an earlier panel stopped the elimination (uniform over the grid)
 
@@ -151,17 +156,19 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
         mbar_fence_init();
         mbar_expect_tx(&bars[0], XBYTES);
         if (nb > 1) mbar_expect_tx(&bars[1], XBYTES);
+        helper_read = 0;
+        stop_s = 0;
     }
     for (int e = t; e < nb * rpcp; e += CP_THREADS) {
         const int c = e / rpcp, i = e - c * rpcp;
         panel[e] = i < nrows ? p.basis[(size_t)(p.t0 + c) * S + row0 + i] : 0.0;
     }
-    double mu[RT];
-    bool ok[RT];
+    double mu[RPL];
+    bool ok[RPL];
 #pragma unroll
-    for (int m = 0; m < RT; ++m) {
-        const int i = ri + tr * m;
-        ok[m] = rowthr && i < nrows;
+    for (int m = 0; m < RPL; ++m) {
+        const int i = lane + 32 * m;
+        ok[m] = warp == 0 && i < nrows;
         mu[m] = ok[m] ? p.mu[row0 + i] : 0.0;
     }
     __syncthreads();
@@ -177,165 +184,188 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
         pt = now_;                        \
     }
 
-    double blk[RT][B];                             // this thread's rows of the current block (row threads)
-    // Ratio test on block column q (registers), CTA-wide argmin, and the post of this CTA's candidate for pivot
-    // column e = b0 + q to all CTAs.  One block barrier.
-    auto test_and_post = [&](int e, const double (&col)[RT]) {
+    double blk[RPL][B];                            // pivot warp: this lane's rows of the current block
+    // Pivot warp: ratio test on block column qc (registers), warp argmin, post of this CTA's candidate for pivot
+    // column e to all CTAs.
+    auto test_and_post = [&](int e, int qc) {
         const int par = e & 1;
         unsigned long long key = CP_NONE;
         double balpha = 0.0, binv = 0.0;
-        int bm = 0;
-        if (rowthr) {
 #pragma unroll
-            for (int m = 0; m < RT; ++m) {
-                if (ok[m] && col[m] > 0.0) {
-                    double y;
-                    const double q = cp_div(mu[m], col[m], y);
-                    const unsigned long long kq = cp_pack(q, ri + tr * m);
-                    if (kq < key) { key = kq; balpha = q; binv = y; bm = m; }
+        for (int m = 0; m < RPL; ++m) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < B; ++q)
+                if (q == qc) v = blk[m][q];        // qc is a compile-time constant at every call site after inlining
+            if (ok[m] && v > 0.0) {
+                double y;
+                const double qq = cp_div(mu[m], v, y);
+                const unsigned long long kq = cp_pack(qq, lane + 32 * m);
+                if (kq < key) { key = kq; balpha = qq; binv = y; }
+            }
+        }
+        const unsigned long long mine = key;
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+        key = ((unsigned long long)mhi << 32) | mlo;
+        const bool have = key != CP_NONE;
+        const int bi = (int)(key & ((1ull << CP_IDX_BITS) - 1));
+        const int mstar = bi >> 5;                 // uniform: which of its rows the winning lane stages
+        if (have && mine == key) {
+            stage[0] = balpha; stage[1] = binv; stage[2] = (double)(row0 + bi); stage[3] = 0.0;
+        }
+        if (have) {
+#pragma unroll
+            for (int m = 0; m < RPL; ++m)
+                if (m == mstar && mine == key) {
+#pragma unroll
+                    for (int q = 0; q < B; ++q) stage[CP_HDR + q] = blk[m][q];
                 }
-            }
-            const unsigned long long mine = key;
-            const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-            const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
-            const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
-            key = ((unsigned long long)mhi << 32) | mlo;
-            if (lane == 0) red_key[par][warp] = key;
-            if (mine == key && key != CP_NONE) {
-                // this lane holds the warp's best row: stage its header and block row (used if the warp wins the CTA)
-                double* st = stage + (size_t)(par * (CP_THREADS / 32) + warp) * HB;
-                st[0] = balpha; st[1] = binv; st[2] = (double)(row0 + (int)(key & ((1ull << CP_IDX_BITS) - 1))); st[3] = 0.0;
-#pragma unroll
-                for (int m = 0; m < RT; ++m)
-                    if (m == bm) {
-#pragma unroll
-                        for (int q = 0; q < B; ++q) st[CP_HDR + q] = blk[m][q];
-                    }
-            }
         }
-        __syncthreads();
-        // CTA winner: every warp resolves it from the per-warp keys; warp w posts to CTA w
-        unsigned long long best = CP_NONE;
-        for (int w = 0; w < nwr; ++w) best = cp_min64(best, red_key[par][w]);
-        int wsel = 0;
-        for (int w = nwr - 1; w >= 0; --w) wsel = red_key[par][w] == best ? w : wsel;
-        const bool have = best != CP_NONE;
-        const double* st = stage + (size_t)(par * (CP_THREADS / 32) + wsel) * HB;
-        const uint32_t dst = cp_mapa(smem_addr(recv + (size_t)(par * P + r) * HB), (uint32_t)warp);
-        const uint32_t bar = cp_mapa(smem_addr(&bars[par]), (uint32_t)warp);
-        if (lane < HB / 2) {
-            double a = st[2 * lane], b = st[2 * lane + 1];
-            if (!have) { a = 0.0; b = 0.0; }
-            if (lane == 1 && !have) a = -1.0;       // header[2] = row index, -1: no candidate
-            cp_st_async2(dst + (uint32_t)lane * 16u, a, b, bar);
+        while (helper_read < e) {
         }
+        __syncwarp();
+        for (int ch = lane; ch < P * (HB / 2); ch += 32) {
+            const int peer = ch / (HB / 2), part = ch - peer * (HB / 2);
+            double a = have ? stage[2 * part] : 0.0, b = have ? stage[2 * part + 1] : 0.0;
+            if (part == 1 && !have) a = -1.0;      // header[2] = row index, -1: no candidate
+            const uint32_t dst = cp_mapa(smem_addr(recv + (size_t)(par * P + r) * HB), (uint32_t)peer);
+            const uint32_t bar = cp_mapa(smem_addr(&bars[par]), (uint32_t)peer);
+            cp_st_async2(dst + (uint32_t)part * 16u, a, b, bar);
+        }
+        __syncwarp();                              // the stage may be rewritten by the next call
+    };
+    // winner of the 8 candidates of exchange s: lowest ratio, then lowest CTA rank (= lowest row); -1: none
+    auto winner = [&](const double* rb, double& alpha) {
+        double al[P];
+        bool va[P];
+#pragma unroll
+        for (int c = 0; c < P; ++c) {
+            const double2 h = *reinterpret_cast<const double2*>(rb + (size_t)c * HB);
+            al[c] = h.x;
+            va[c] = rb[(size_t)c * HB + 2] >= 0.0;
+        }
+        int wi[P];
+#pragma unroll
+        for (int c = 0; c < P; ++c) wi[c] = va[c] ? c : -1;
+#pragma unroll
+        for (int w = 1; w < P; w *= 2)
+#pragma unroll
+            for (int c = 0; c + w < P; c += 2 * w) {
+                const bool take = wi[c + w] >= 0 && (wi[c] < 0 || al[c + w] < al[c]);
+                al[c] = take ? al[c + w] : al[c];
+                wi[c] = take ? wi[c + w] : wi[c];
+            }
+        alpha = al[0];
+        return wi[0];
     };
 
     int done = 0;
     bool stopped = false;
-    for (int b0 = 0; b0 < nb && !stopped; b0 += B) {
+    for (int b0 = 0; b0 < nb; b0 += B) {
         const int bw = min(B, nb - b0);
         const int glen = nb - (b0 + bw);           // columns of the panel to the right of this block
-        // ---- block start: registers <- panel, first ratio test ----
+        if (warp == 0) {
 #pragma unroll
-        for (int m = 0; m < RT; ++m) {
-#pragma unroll
-            for (int q = 0; q < B; ++q) blk[m][q] = (ok[m] && q < bw) ? panel[(size_t)(b0 + q) * rpcp + ri + tr * m] : 0.0;
-        }
-        if (t == 0 && glen > 0) mbar_expect_tx(&gbar, (uint32_t)(bw * glen * 8));
-        {
-            double col[RT];
-#pragma unroll
-            for (int m = 0; m < RT; ++m) col[m] = blk[m][0];
-            test_and_post(b0, col);
-        }
-        CP_TICK(4)
-        int jblk[B];
-#pragma unroll
-        for (int q = 0; q < B; ++q) {
-            if (q < bw && !stopped) {
-                const int s = b0 + q, par = s & 1;
-                mbar_wait(&bars[par], (uint32_t)((s >> 1) & 1));
-                CP_TICK(0)
-                const double* rb = recv + (size_t)par * P * HB;
-                // winner of the 8 candidates: lowest ratio, then lowest CTA rank (= lowest row)
-                int wr = -1;
-                double alpha = 0.0;
-#pragma unroll
-                for (int c = P - 1; c >= 0; --c) {
-                    const double2 h = *reinterpret_cast<const double2*>(rb + (size_t)c * HB);
-                    const double jr = rb[(size_t)c * HB + 2];
-                    const bool valid = jr >= 0.0;
-                    if (valid && (wr < 0 || h.x <= alpha)) { wr = c; alpha = h.x; }
-                }
-                if (wr < 0) { stopped = true; }
-                else {
-                    const double* wb = rb + (size_t)wr * HB;
-                    const double inv = wb[1];
-                    const int jg = (int)wb[2];
-                    jblk[q] = jg;
-                    done = s + 1;
-                    double rowv[B];
-#pragma unroll
-                    for (int qq = 0; qq < B; qq += 2) {
-                        const double2 v2 = *reinterpret_cast<const double2*>(wb + CP_HDR + qq);
-                        rowv[qq] = v2.x;
-                        rowv[qq + 1] = v2.y;
-                    }
-                    // the arming of this barrier for exchange s + 2 and the in-block multipliers (uniform values)
-                    if (t == 0 && s + 2 < nb) mbar_expect_tx(&bars[par], XBYTES);
-                    if (warp == CP_THREADS / 32 - 1 && lane < B) lblk[q * B + lane] = lane < q ? wb[CP_HDR + lane] : 0.0;
-                    double col[RT];
-#pragma unroll
-                    for (int m = 0; m < RT; ++m) {
-                        const double v = blk[m][q];
-                        const bool pv = ok[m] && (row0 + ri + tr * m == jg);
-                        const double u = pv ? 1.0 : v * inv;
-                        blk[m][q] = u;
-                        mu[m] = pv ? 0.0 : fma(-alpha, v, mu[m]);
-#pragma unroll
-                        for (int qq = q + 1; qq < B; ++qq) blk[m][qq] = pv ? 0.0 : fma(-u, rowv[qq], blk[m][qq]);
-                        col[m] = q + 1 < B ? blk[m][q + 1 < B ? q + 1 : q] : 0.0;
-                    }
-                    CP_TICK(1)
-                    if (q + 1 < bw) test_and_post(s + 1, col);
-                    CP_TICK(2)
-                    // off the critical path: the owner of the pivot row sends its (not yet updated) entries of the
-                    // columns right of the block to every CTA; they are brought up to date at the end of the block
-                    if (glen > 0 && jg >= row0 && jg < row0 + nrows) {
-                        const uint32_t gdst = cp_mapa(smem_addr(gbuf), (uint32_t)warp);
-                        const uint32_t gb = cp_mapa(smem_addr(&gbar), (uint32_t)warp);
-                        for (int c = lane; c < glen; c += 32)
-                            cp_st_async(gdst + (uint32_t)((size_t)c * B + q) * 8u,
-                                        panel[(size_t)(b0 + bw + c) * rpcp + (jg - row0)], gb);
-                    }
-                    if (r == 0 && t == 0) p.piv[p.t0 + s] = jg;
-                    CP_TICK(3)
-                }
-            }
-        }
-        if (stopped) break;
-        // ---- block end: u columns to the panel, R = L^-1 G, rank-bw update of the columns right of the block ----
-#pragma unroll
-        for (int m = 0; m < RT; ++m)
-            if (ok[m]) {
+            for (int m = 0; m < RPL; ++m)
 #pragma unroll
                 for (int q = 0; q < B; ++q)
-                    if (q < bw) panel[(size_t)(b0 + q) * rpcp + ri + tr * m] = blk[m][q];
+                    blk[m][q] = (ok[m] && q < bw) ? panel[(size_t)(b0 + q) * rpcp + lane + 32 * m] : 0.0;
+            if (lane == 0 && glen > 0) mbar_expect_tx(&gbar, (uint32_t)(bw * glen * 8));
+            test_and_post(b0, 0);
+            CP_TICK(4)
+        }
+        if (warp <= 1) {
+#pragma unroll
+            for (int q = 0; q < B; ++q) {
+                if (q < bw && !stopped) {
+                    const int s = b0 + q, par = s & 1;
+                    mbar_wait(&bars[par], (uint32_t)((s >> 1) & 1));
+                    CP_TICK(0)
+                    const double* rb = recv + (size_t)par * P * HB;
+                    double alpha;
+                    const int wr = winner(rb, alpha);
+                    if (wr < 0) {
+                        stopped = true;
+                    } else {
+                        const double* wb = rb + (size_t)wr * HB;
+                        const double inv = wb[1];
+                        const int jg = (int)wb[2];
+                        done = s + 1;
+                        if (warp == 0) {
+                            double rowv[B];
+#pragma unroll
+                            for (int qq = 0; qq < B; qq += 2) {
+                                const double2 v2 = *reinterpret_cast<const double2*>(wb + CP_HDR + qq);
+                                rowv[qq] = v2.x;
+                                rowv[qq + 1] = v2.y;
+                            }
+                            if (lane == 0 && s + 2 < nb) mbar_expect_tx(&bars[par], XBYTES);
+#pragma unroll
+                            for (int m = 0; m < RPL; ++m) {
+                                const double v = blk[m][q];
+                                const bool pv = ok[m] && (row0 + lane + 32 * m == jg);
+                                const double u = pv ? 1.0 : v * inv;
+                                blk[m][q] = u;
+                                mu[m] = pv ? 0.0 : fma(-alpha, v, mu[m]);
+#pragma unroll
+                                for (int qq = q + 1; qq < B; ++qq)
+                                    blk[m][qq] = pv ? 0.0 : fma(-u, rowv[qq], blk[m][qq]);
+                            }
+                            CP_TICK(1)
+                            if (q + 1 < bw) test_and_post(s + 1, q + 1);
+                            CP_TICK(2)
+                        } else {
+                            // helper: multipliers of this pivot row inside the block, the pivot, then release the buffer
+                            if (lane < B) lblk[q * B + lane] = lane < q ? wb[CP_HDR + lane] : 0.0;
+                            if (lane == 0) {
+                                jblk_s[q] = jg;
+                                if (r == 0) p.piv[p.t0 + s] = jg;
+                            }
+                            __syncwarp();
+                            if (lane == 0) helper_read = s + 1;
+                            // the owner of the pivot row sends its (not yet updated) entries of the columns right of
+                            // the block to every CTA; they are brought up to date at the end of the block
+                            if (glen > 0 && jg >= row0 && jg < row0 + nrows) {
+                                for (int idx = lane; idx < glen * P; idx += 32) {
+                                    const int c = idx / P, peer = idx - c * P;
+                                    const uint32_t gdst = cp_mapa(smem_addr(gbuf + (size_t)c * B + q), (uint32_t)peer);
+                                    const uint32_t gb = cp_mapa(smem_addr(&gbar), (uint32_t)peer);
+                                    cp_st_async(gdst, panel[(size_t)(b0 + bw + c) * rpcp + (jg - row0)], gb);
+                                }
+                            }
+                        }
+                    }
+                }
             }
+            if (warp == 1 && stopped && lane == 0) helper_read = nb + 1;
+            if (warp == 0) {
+                if (stopped && lane == 0) stop_s = 1;
+                // u columns of the block -> panel (U of the trailing update, L rows, multipliers of the rank-8 update)
+                if (!stopped) {
+#pragma unroll
+                    for (int m = 0; m < RPL; ++m)
+                        if (ok[m]) {
+#pragma unroll
+                            for (int q = 0; q < B; ++q)
+                                if (q < bw) panel[(size_t)(b0 + q) * rpcp + lane + 32 * m] = blk[m][q];
+                        }
+                }
+                CP_TICK(3)
+            }
+        }
+        __syncthreads();                           // (A) u columns, L, pivots of the block and the stop flag are visible
+        if (stop_s) break;
         if (glen > 0) mbar_wait(&gbar, (uint32_t)((b0 / B) & 1));
-        __syncthreads();
         CP_TICK(5)
         if (p.write_u && warp == CP_THREADS / 32 - 1) {
             // rows of L for the trailing-column solve, written by the CTA that owns the pivot row
-#pragma unroll
-            for (int q = 0; q < B; ++q) {
-                if (q < bw) {
-                    const int jg = jblk[q];
-                    if (jg >= row0 && jg < row0 + nrows)
-                        for (int cc = lane; cc < b0 + q; cc += 32)
-                            p.lmat[(size_t)(b0 + q) * CP_NB + cc] = panel[(size_t)cc * rpcp + (jg - row0)];
-                }
+            for (int q = 0; q < bw; ++q) {
+                const int jg = jblk_s[q];
+                if (jg >= row0 && jg < row0 + nrows)
+                    for (int cc = lane; cc < b0 + q; cc += 32)
+                        p.lmat[(size_t)(b0 + q) * CP_NB + cc] = panel[(size_t)cc * rpcp + (jg - row0)];
             }
         }
         if (glen > 0) {
@@ -351,60 +381,53 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
 #pragma unroll
                 for (int q = 0; q < B; ++q) gp[q] = rr[q];
             }
-            __syncthreads();
-            // all threads: rows ri (+ tr m), columns ci, ci + tc, ...
-            double uu[RT][B];
-            bool okk[RT], dd[RT];
+            __syncthreads();                       // (B) R complete
+            // all threads: row ri, columns ci, ci + tc, ...
+            double uu[B];
+            const bool okk = ri < nrows;
+            bool dd = false;
 #pragma unroll
-            for (int m = 0; m < RT; ++m) {
-                const int i = ri + tr * m;
-                okk[m] = i < nrows;
-                dd[m] = false;
-#pragma unroll
-                for (int q = 0; q < B; ++q) {
-                    uu[m][q] = (okk[m] && q < bw) ? panel[(size_t)(b0 + q) * rpcp + i] : 0.0;
-                    if (q < bw && okk[m] && row0 + i == jblk[q]) dd[m] = true;
-                }
+            for (int q = 0; q < B; ++q) {
+                uu[q] = (okk && q < bw) ? panel[(size_t)(b0 + q) * rpcp + ri] : 0.0;
+                if (q < bw && okk && row0 + ri == jblk_s[q]) dd = true;
             }
-            for (int c = ci; c < glen; c += tc) {
-                double rr[B];
-                const double2* gp = reinterpret_cast<const double2*>(gbuf + (size_t)c * B);
+            if (okk) {
+                for (int c = ci; c < glen; c += tc) {
+                    double rr[B];
+                    const double2* gp = reinterpret_cast<const double2*>(gbuf + (size_t)c * B);
 #pragma unroll
-                for (int q = 0; q < B; q += 2) {
-                    const double2 v2 = gp[q / 2];
-                    rr[q] = v2.x;
-                    rr[q + 1] = v2.y;
-                }
-#pragma unroll
-                for (int m = 0; m < RT; ++m) {
-                    if (okk[m]) {
-                        double* x = panel + (size_t)(b0 + bw + c) * rpcp + ri + tr * m;
-                        double acc = *x;
-#pragma unroll
-                        for (int q = 0; q < B; ++q) acc = fma(-uu[m][q], rr[q], acc);
-                        *x = dd[m] ? 0.0 : acc;
+                    for (int q = 0; q < B; q += 2) {
+                        const double2 v2 = gp[q / 2];
+                        rr[q] = v2.x;
+                        rr[q + 1] = v2.y;
                     }
+                    double* x = panel + (size_t)(b0 + bw + c) * rpcp + ri;
+                    double acc = *x;
+#pragma unroll
+                    for (int q = 0; q < B; ++q) acc = fma(-uu[q], rr[q], acc);
+                    *x = dd ? 0.0 : acc;
                 }
             }
-            __syncthreads();
+            __syncthreads();                       // (C) the rest of the panel is up to date
         }
         CP_TICK(6)
     }
 #undef CP_TICK
     __syncthreads();
-    if (rowthr) {
+    const bool stopped_all = stop_s != 0;
+    if (warp == 0) {
 #pragma unroll
-        for (int m = 0; m < RT; ++m)
-            if (ok[m]) p.mu[row0 + ri + tr * m] = mu[m];
+        for (int m = 0; m < RPL; ++m)
+            if (ok[m]) p.mu[row0 + lane + 32 * m] = mu[m];
     }
-    if (p.write_u && !stopped) {
+    if (p.write_u && !stopped_all) {
         for (int e = t; e < nb * rpcp; e += CP_THREADS) {
             const int c = e / rpcp, i = e - c * rpcp;
             if (i < nrows) p.basis[(size_t)(p.t0 + c) * S + row0 + i] = panel[e];
         }
     }
     if (r == 0 && t == 0) {
-        if (stopped) p.state[0] = 1;
+        if (stopped_all) p.state[0] = 1;
         p.state[1] = p.t0 + done;
         if (p.prof)
             for (int i = 0; i < 8; ++i) p.prof[i] += pa[i];
@@ -515,18 +538,18 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
 }
 
 struct PanelPlan {
-    int rt, rpc, rpcp, tr, nb;
+    int rpl, rpc, rpcp, tr, nb;
     bool single;
     size_t smem(int nb_) const {
-        return ((size_t)nb_ * rpcp + 2 * (size_t)CP_P * CP_HB + (size_t)nb_ * CP_B + CP_B * CP_B + 2 * 8 * CP_HB) * 8;
+        return ((size_t)nb_ * rpcp + 2 * (size_t)CP_P * CP_HB + (size_t)nb_ * CP_B + CP_B * CP_B + CP_HB) * 8;
     }
 };
 
 static bool plan_panel(int S, int k, int nb_hint, PanelPlan* pl) {
     if (S <= 0 || k <= 0 || k >= S + 1) return false;
     pl->rpc = (S + CP_P - 1) / CP_P;
-    if (pl->rpc > 2 * CP_THREADS) return false;
-    pl->rt = pl->rpc > CP_THREADS ? 2 : 1;
+    if (pl->rpc > CP_THREADS) return false;             // S <= 2048: the pivot warp holds 8 rows per lane at most
+    pl->rpl = pl->rpc <= 32 ? 1 : (pl->rpc <= 64 ? 2 : (pl->rpc <= 128 ? 4 : 8));
     int tr = 32;
     while (tr < pl->rpc && tr < CP_THREADS) tr *= 2;
     pl->tr = tr;
@@ -574,16 +597,19 @@ extern "C" int sober_car_panel_profiled(double* basis, int32_t k, int32_t S, dou
     double* Rt = lmat + CP_NB * CP_NB;
     SOBER_CUDA_CHECK(cudaMemsetAsync(state, 0, 16, st));
 
-    void (*kern)(const CarPanelParams) = pl.rt == 1 ? car_panel_kernel<1> : car_panel_kernel<2>;
+    void (*kern)(const CarPanelParams) = pl.rpl == 1 ? car_panel_kernel<1>
+                                         : (pl.rpl == 2 ? car_panel_kernel<2>
+                                                        : (pl.rpl == 4 ? car_panel_kernel<4> : car_panel_kernel<8>));
+    const int kvar = pl.rpl == 1 ? 0 : (pl.rpl == 2 ? 1 : (pl.rpl == 4 ? 2 : 3));
     const size_t smem_max = pl.smem(pl.single ? k : pl.nb);
     {   // the > 48 KB opt-in is per device and sticky: once per (device, kernel variant), never inside a graph capture
-        static int configured[64][2] = {};
+        static int configured[64][4] = {};
         static int configured_upd[64] = {};
         int dev = 0;
         SOBER_CUDA_CHECK(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 64 || configured[dev][pl.rt - 1] < (int)smem_max) {
+        if (dev < 0 || dev >= 64 || configured[dev][kvar] < (int)smem_max) {
             SOBER_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_MAX));
-            if (dev >= 0 && dev < 64) configured[dev][pl.rt - 1] = CP_SMEM_MAX;
+            if (dev >= 0 && dev < 64) configured[dev][kvar] = CP_SMEM_MAX;
         }
         if (dev < 0 || dev >= 64 || !configured_upd[dev]) {
             SOBER_CUDA_CHECK(cudaFuncSetAttribute(car_panel_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

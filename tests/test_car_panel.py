@@ -29,7 +29,7 @@ def problem(S, n_prime, seed, decades=4):
 # (S, n', nb_hint): nb_hint 0 = automatic (single panel when it fits), else forced panel width
 SHAPES = [(400, 200, 0), (200, 100, 0), (33, 7, 0), (96, 41, 0), (401, 199, 0), (17, 16, 0),
           (400, 200, 64), (400, 200, 24), (200, 100, 8), (130, 61, 64),
-          (1000, 500, 0), (2000, 1000, 0), (2000, 1001, 0), (1536, 600, 32), (3000, 1500, 0)]
+          (1000, 500, 0), (2000, 1000, 0), (2000, 1001, 0), (1536, 600, 32), (2048, 1024, 0), (777, 390, 0)]
 
 
 @pytest.mark.parametrize("S,n_prime,nb", SHAPES)
@@ -52,6 +52,12 @@ def test_car_panel_matches_oracle_elimination(ops, cuda_device, S, n_prime, nb):
     assert float((design.T @ got - design.T @ mass).abs().max()) < 1e-11
     assert torch.equal(got > 0, want > 0)
     assert float((got - want).abs().max()) < 1e-9
+
+
+def test_car_panel_shape_limit(ops):
+    """S <= 2048 (eight rows per lane of the pivot warp); larger problems stay with the whole-GPU kernel."""
+    assert ops.car_panel_fits(2048, 1024) == 2 and ops.car_panel_fits(2049, 1024) == 0
+    assert ops.car_panel_fits(400, 200) == 1
 
 
 def test_car_panel_early_stop_guard(ops, cuda_device):

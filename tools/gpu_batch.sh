@@ -16,6 +16,8 @@ for step in "$@"; do
     smoke)    run smoke python __graft_entry__.py smoke ;;
     ncuk1)    TMO=600 run ncu_k1 ncu --set full --clock-control none --import-source on -k regex:group_records -s 4 -c 1 -f -o $OUT/k1prof python tools/k1_time.py ;;
     ncusmoke) TMO=600 TAILN=60 run ncu_smoke ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_smoke.csv python -c "import __graft_entry__ as g; g.smoke()" ;;
+    parbrk)   TAILN=20 run parity_breakdown python tools/parity_breakdown.py ;;
+    ncucar)   TMO=600 TAILN=5 run ncu_car ncu --metrics gpu__time_duration.sum --clock-control none -k regex:car_panel -c 400 --csv --log-file $OUT/launches_car.csv python tools/time_car.py ;;
     stagepar) TAILN=25 run stage_c2_parity python tools/stage_breakdown.py c2 parity ;;
     bench2)   TMO=600 TAILN=3 run bench_c2 python bench.py --steps 10 --warmup 3 ;;
     bench5)   TMO=600 TAILN=3 run bench_c5 python bench.py --workload c5 --steps 5 --warmup 2 --no-cpu-baseline ;;

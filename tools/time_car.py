@@ -57,5 +57,5 @@ for S, n_prime, nb in shapes:
     ops.car_panel(r, m, nb_hint=nb, prof=prof)
     torch.cuda.synchronize()
     p = prof.tolist()
-    print("      panel-kernel cycles/step (CTA 0): wait %.0f | winner+update %.0f | ratio+argmin+post %.0f | G send %.0f | block-start test %.0f | block end: gbar+sync %.0f, solve+update %.0f"
+    print("      panel-kernel cycles/step (CTA 0, pivot warp): wait %.0f | winner+update %.0f | ratio+argmin+post %.0f | u columns %.0f | block-start test %.0f | block end: barrier+G wait %.0f, solve+update %.0f"
           % (p[0] / k, p[1] / k, p[2] / k, p[3] / k, p[4] / k, p[5] / k, p[6] / k))
