@@ -325,6 +325,45 @@ def parity_block(runner, sample_n):
     return out
 
 
+def sharded_parity(dev, rank, world):
+    """N > 1: the row-sharded run (NCCL all-reduce of the group sums) against the single-GPU run of the SAME global
+    input on rank 0 -- a small C2-shaped fixture, before anything is timed.  Summation order differs between the two
+    (per-rank partial sums), so weights agree to rounding and indices wherever no near-tie exists."""
+    import torch.distributed as dist
+    import sober_b200
+    n_per, L, b = 20_000, 300, 64
+    X, mu = synth("c2", n_per, 300 + rank, dev)
+    tot = mu.sum()
+    dist.all_reduce(tot)
+    mu /= tot
+    Z = X[:L].clone()
+    dist.broadcast(Z, 0)
+    kern = make_kernel("c2", dev)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(7)
+        idx_s, w_s = sober_b200.recombination(X, Z, b, kern, dev, torch.float64, init_weights=mu.clone())
+    xs = [torch.empty_like(X) for _ in range(world)]
+    ms = [torch.empty_like(mu) for _ in range(world)]
+    dist.all_gather(xs, X)
+    dist.all_gather(ms, mu)
+    out = None
+    if rank == 0:
+        sober_b200.set_communicator(None)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            torch.manual_seed(7)
+            idx_1, w_1 = sober_b200.recombination(torch.cat(xs), Z, b, kern, dev, torch.float64,
+                                                  init_weights=torch.cat(ms))
+        sober_b200.enable_sharding()
+        same = bool(torch.equal(idx_s, idx_1))
+        out = {"n_total": n_per * world, "n_nys": L, "batch": b, "indices_identical": same,
+               "max_dw": float((w_s - w_1).abs().max()) if same else None,
+               "what": "row-sharded run over %d ranks vs the same global input on rank 0 alone" % world}
+    dist.barrier()
+    return out
+
+
 def reference_gpu_leg(runner, flush):
     """The reference algorithm's own PyTorch path (oracle port, op for op SOBER/_rchq.py) executing on THIS GPU on the
     full workload (the same-box comparison).  One warm-up on a small sample, one timed call."""
@@ -434,6 +473,7 @@ def main():
     ops = _rchq._ops()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     sober_b200.options.set_mode(args.mode)
+    shard_check = sharded_parity(dev, rank, world) if (world > 1 and not args.no_extras) else None
     run = Runner(name, dev, rank, world, args.pred_cov)
 
     # ---- timed region: K steps, inputs resident in HBM ----
@@ -575,6 +615,8 @@ def main():
                                  if k not in ("car_panel", "car_cols", "car_cluster") or "car_step_graph" not in timing)
     out["stage_ms_per_step"]["other (range finder, projection GEMM, host syncs, launch gaps)"] = unattributed
     out.update(extras)
+    if shard_check is not None:
+        out["sharded_parity"] = shard_check
     if world == 1 and not args.no_extras and args.mode == "fast" and name in ("c1", "c2", "c3"):
         sample = min(args.cpu_sample if args.cpu_sample > 0 else 100_000, n_rec)
         out["parity"] = parity_block(run, sample)

@@ -266,8 +266,6 @@ class Recombiner:
         row0, n_total = sum(counts[:comm.rank]), sum(counts)
         if n_total >= 2 ** 31:
             raise ValueError("sober_b200 supports fewer than 2^31 candidates")
-        if calc_obj is not None and comm.world > 1:
-            raise NotImplementedError("calc_obj with sharded candidates")
 
         if init_weights is None:
             mu = torch.full((n_rows,), 1.0, dtype=torch.float64, device=dev) / n_total
@@ -371,7 +369,7 @@ class Recombiner:
 
         while True:
             if remaining <= S:
-                sel_idx, sel_w = self._finish(st, alive, n_local, pos0, remaining, n, UextT, row0, obj)
+                sel_idx, sel_w = self._finish(st, alive, n_local, pos0, remaining, n, UextT, row0, obj, n_rows)
                 clock.lap("finish")
                 break
             E = remaining // S
@@ -383,19 +381,25 @@ class Recombiner:
             objs = None
             if obj is not None:
                 objs = torch.zeros((S, 1), dtype=torch.float64, device=dev)
-                row = obj[idx.long()].reshape(1, -1).contiguous()
-                ops.group_accumulate_gram(row, mass, pos0, ES, S, objs, None)
-                if t0 < n_local:
-                    extra[Lp + 1] = torch.dot(row[0, t0:], mass[t0:])
+                if n_local > 0:
+                    row = obj[idx.long()].reshape(1, -1).contiguous()
+                    ops.group_accumulate_gram(row, mass, pos0, ES, S, objs, None)
+                    if t0 < n_local:
+                        extra[Lp + 1] = torch.dot(row[0, t0:], mass[t0:])
             if comm.world > 1:
-                packed = torch.cat([at.reshape(-1), totw, extra])
+                # ONE all-reduce per iteration: group sums, group masses, the remainder's second count and -- with an
+                # objective (SOBER/_rchq.py:138-150) -- the per-group objective sums ride in the same packed buffer
+                parts = [at.reshape(-1), totw, extra] + ([objs.reshape(-1)] if objs is not None else [])
+                packed = torch.cat(parts)
                 t_ar = ops._begin("all_reduce") if hasattr(ops, "_begin") else None
                 comm.all_reduce(packed)
                 if t_ar is not None:
                     ops._end("all_reduce", t_ar, packed.numel() * 8)
                 at = packed[:S * Lp].reshape(S, Lp)
                 totw = packed[S * Lp:S * Lp + S]
-                extra = packed[S * Lp + S:]
+                extra = packed[S * Lp + S:S * Lp + S + Lp + 3]
+                if objs is not None:
+                    objs = packed[S * Lp + S + Lp + 3:].reshape(S, 1)
             # The fused DMMA projection kernel (csrc/project.cu) is correct but was measured 7x slower than the cuBLAS
             # DGEMM + 4 elementwise ops it replaces (0.14 ms vs 0.02 ms per call at C2); it stays opt-in.
             fused = (o.fused_projection and obj is None and self.trace is None and hasattr(ops, "project_design"))
@@ -468,7 +472,7 @@ class Recombiner:
         return sel_idx, sel_w
 
     # -----------------------------------------------------------------------------------------------------
-    def _finish(self, st, alive, n_local, pos0, remaining, n, UextT, row0, obj):
+    def _finish(self, st, alive, n_local, pos0, remaining, n, UextT, row0, obj, n_rows=0):
         """The two terminal branches, SOBER/_rchq.py:72-75 (R <= n+1) and :77-114 (n+1 < R <= S)."""
         ops, comm, o = self.ops, self.comm, self.opts
         dev = ops.device
@@ -493,8 +497,19 @@ class Recombiner:
             comm.all_reduce(all_mass)
             comm.all_reduce(all_idx)
         feats = feats_t @ UextT                                                            # (R x n)
+        head_obj = None
         if obj is not None:
-            alive_obj = obj[all_idx]
+            # objective values of the remaining points, and -- for the reference's position-indexed lookup below -- of
+            # the first ``remaining`` ROWS of the global candidate set; both assembled from the row shards
+            alive_obj = torch.zeros(remaining, dtype=torch.float64, device=dev)
+            alive_obj[pos0:pos0 + n_local] = obj[idx.long()]
+            head_obj = torch.zeros(remaining, dtype=torch.float64, device=dev)
+            lo, hi = min(row0, remaining), min(row0 + (n_rows or obj.numel()), remaining)
+            if hi > lo:
+                head_obj[lo:hi] = obj[lo - row0:hi - row0]
+            if comm.world > 1:
+                comm.all_reduce(alive_obj)
+                comm.all_reduce(head_obj)
             feats = torch.cat([feats, alive_obj.unsqueeze(1)], 1)
         if self.nullspace is None and o.nullspace == "projector":
             wfull, _, summary, _ = _car.reduce_step(ops, feats, all_mass,
@@ -507,7 +522,7 @@ class Recombiner:
         if obj is not None:
             # NB the reference indexes ``obj`` with POSITIONS here (SOBER/_rchq.py:89), kept as is
             live = torch.nonzero(wfull > 0).reshape(-1)
-            wfull = self._objective_step(feats[:, :n], None, wfull, obj_vals=obj[live])
+            wfull = self._objective_step(feats[:, :n], None, wfull, obj_vals=head_obj[live])
         live = wfull > 0
         return all_idx[live], wfull[live]
 

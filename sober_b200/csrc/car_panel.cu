@@ -198,11 +198,19 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
             for (int q = 0; q < B; ++q)
                 if (q == qc) v = blk[m][q];        // qc is a compile-time constant at every call site after inlining
             if (ok[m] && v > 0.0) {
+                // ranking key from a 2^-44-accurate quotient (MUFU seed + one Newton step; the key keeps 40 bits); the
+                // exact quotient and reciprocal are computed once, for the lane's best row
                 double y;
-                const double qq = cp_div(mu[m], v, y);
-                const unsigned long long kq = cp_pack(qq, lane + 32 * m);
-                if (kq < key) { key = kq; balpha = qq; binv = y; }
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+                y = fma(y, fma(-v, y, 1.0), y);
+                const unsigned long long kq = cp_pack(mu[m] * y, lane + 32 * m);
+                if (kq < key) { key = kq; balpha = mu[m]; binv = v; }
             }
+        }
+        if (key != CP_NONE) {
+            double y;
+            balpha = cp_div(balpha, binv, y);
+            binv = y;
         }
         const unsigned long long mine = key;
         const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
@@ -500,6 +508,8 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
         const int j = piv[t0 + t] - i0;
         if (j >= 0 && j < CU_TI) is_piv[j] = 1;
     }
+    // thread (ti, tcx): rows i0 + 32 q + 2 ti + {0, 1} (q < 4: consecutive lanes read consecutive 16-byte chunks of U --
+    // with 8 adjacent rows per thread the LDS.128 were 4-way bank-conflicted and the kernel took 45 us), columns 4 tcx + jj
     const int ti = t & 15, tcx = t >> 4;
     double acc[4][8];
 #pragma unroll
@@ -509,10 +519,10 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
 #pragma unroll 4
     for (int s = 0; s < CP_NB; ++s) {
         double a[8], b[4];
-        const double2* ap = reinterpret_cast<const double2*>(Us + s * CU_TI + ti * 8);
+        const double2* ap = reinterpret_cast<const double2*>(Us + s * CU_TI + ti * 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const double2 v = ap[q];
+            const double2 v = ap[q * 16];
             a[2 * q] = v.x;
             a[2 * q + 1] = v.y;
         }
@@ -528,11 +538,11 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
     for (int jj = 0; jj < 4; ++jj) {
         const int c = c0 + tcx * 4 + jj;
         if (c >= k) continue;
-        double* dst = basis + (size_t)c * S + i0 + ti * 8;
+        double* col = basis + (size_t)c * S + i0;
 #pragma unroll
         for (int ii = 0; ii < 8; ++ii) {
-            const int i = i0 + ti * 8 + ii;
-            if (i < S) dst[ii] = is_piv[ti * 8 + ii] ? 0.0 : dst[ii] - acc[jj][ii];
+            const int il = (ii >> 1) * 32 + ti * 2 + (ii & 1);
+            if (i0 + il < S) col[il] = is_piv[il] ? 0.0 : col[il] - acc[jj][ii];
         }
     }
 }

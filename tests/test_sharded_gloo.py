@@ -28,14 +28,20 @@ def _worker(rank, world, port, name, split, out):
             warnings.simplefilter("ignore")
             torch.manual_seed(7)
             idx, w = Recombiner(TorchOps(), comm=Sharded(), opts=opts).run(
-                case.X[lo:hi].clone(), case.Z, case.b, case.kernel(), init_weights=mu)
+                case.X[lo:hi].clone(), case.Z, case.b, case.kernel(), init_weights=mu, calc_obj=case.objective)
         out[rank] = (idx.clone(), w.clone(), None if mu is None else mu.clone())
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("name,split", [("matern6d_rest", 1234), ("predcov_matern6d", 3000),
-                                        ("direct_branch", 17), ("tanimoto256", 5)])
+                                        ("direct_branch", 17), ("tanimoto256", 5),
+                                        # calc_obj branch (SOBER/_rchq.py:67-69,138-150,169-196) with sharded candidates:
+                                        # the per-group objective sums ride in the packed all-reduce; split = 100 puts
+                                        # the position-indexed objective lookup of :89 across both shards
+                                        ("objective_matern4d", 2000), ("objective_matern4d", 100),
+                                        # a rank whose weights are all zero (no alive rows on a shard)
+                                        ("matern6d_rest", 0)])
 def test_two_rank_shard_equals_single_process(name, split):
     port = 29500 + (os.getpid() + hash(name)) % 2000
     manager = mp.Manager()
