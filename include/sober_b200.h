@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SOBER_B200_ABI_VERSION 1
+#define SOBER_B200_ABI_VERSION 2   /* 2: car_panel, gp_rows, popc_probe added; sober_group_args unchanged since 1 */
 
 enum sober_status {
     SOBER_OK = 0,
@@ -264,6 +264,20 @@ int sober_cholesky_upper(const double* G, int64_t ldg, int32_t q, double* R, int
  * ------------------------------------------------------------------------------------------------- */
 int sober_kmeans_assign(const double* X, int64_t ldx, int64_t n, int32_t d, const double* C, int32_t K, int64_t* labels,
                         void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * pi evaluation over the candidate set (SOBER/_gp.py:212-238 `predict`, SOBER/_pi.py:20-38
+ * `PI.lfi`): the per-candidate epilogue of the GP posterior.  K (m x n_obs, ldk) = k(x_i, Xobs_j) from
+ * sober_group_accumulate in Gram mode, T (m x n_obs, ldt) = K W with W = (K_obs + noise I)^-1 (may be NULL: mean only),
+ * alpha (n_obs) = W (y - c):
+ *   mean[i] = mean_const + sum_j K[i,j] alpha[j]
+ *   var[i]  = max(min_var, (kxx ? kxx[i] : kxx_const) - sum_j K[i,j] T[i,j] + noise)
+ *   pi[i]   = Phi((mean[i] - eta) / sqrt(var[i]))
+ * Any of mean / var / pi may be NULL.  One warp per row, one streaming pass over the two tiles.
+ * ------------------------------------------------------------------------------------------------- */
+int sober_gp_rows(const double* K, int64_t ldk, const double* T, int64_t ldt, const double* alpha, int64_t m,
+                  int32_t n_obs, double mean_const, const double* kxx, double kxx_const, double noise, double min_var,
+                  double eta, double* mean, double* var, double* pi, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Stream confined to all SMs of the current device but `reserve_sms` (a CUDA green context; created on first use,

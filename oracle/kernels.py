@@ -153,9 +153,24 @@ class _Strategy:
         self.mean_cache = mean_cache
 
 
+class _Dist:
+    """What ``model(x)`` / ``likelihood(model(x))`` return as far as SOBER/_pi.py:15 looks: ``.loc``, ``.mean``,
+    ``.variance``."""
+
+    def __init__(self, loc, variance):
+        self.loc = self.mean = loc
+        self.variance = variance
+
+
 class _Noise:
     def __init__(self, noise):
         self.noise = noise
+
+    def __call__(self, dist):                      # Gaussian likelihood: adds the observation noise
+        return _Dist(dist.loc, dist.variance + self.noise)
+
+    def eval(self):
+        return self
 
 
 class _ConstMean:
@@ -189,6 +204,14 @@ class GPModel:
 
     def eval(self):
         return self
+
+    def __call__(self, x):
+        """Exact posterior at ``x`` (mean ``c + k alpha``, variance ``k(x,x) - k W k``, no observation noise)."""
+        k_xo = self.covar_module.forward(x, self.train_inputs[0])
+        root = self.prediction_strategy.covar_cache
+        mean = self.mean_module.constant + k_xo @ self.prediction_strategy.mean_cache
+        var = torch.diagonal(self.covar_module.forward(x, x)) - ((k_xo @ root) ** 2).sum(-1)
+        return _Dist(mean, var)
 
 
 def covariance_cache(model):

@@ -10,9 +10,10 @@ from ._settings import configure, options
 from ._install import install, uninstall
 from ._wkde import wkde_pdf
 from ._kmeans import kmeans
+from ._predict import gp_posterior, pi_lfi, predict
 
 __all__ = ["recombination", "install", "uninstall", "configure", "options", "Recombiner", "Sharded",
-           "SingleProcess", "set_communicator", "enable_sharding", "wkde_pdf", "kmeans"]
+           "SingleProcess", "set_communicator", "enable_sharding", "wkde_pdf", "kmeans", "gp_posterior", "pi_lfi", "predict"]
 __version__ = "0.1.0"
 
 

@@ -27,6 +27,17 @@ class KernelSpec:
     mode: str                        # "kernel" | "predictive_covariance"
     x_obs: Optional[torch.Tensor] = None     # (n_obs, d) training inputs      (predictive covariance)
     woodbury: Optional[torch.Tensor] = None  # (n_obs, n_obs)  S S^T           (SOBER/_gp.py:255-278)
+    alpha: Optional[torch.Tensor] = None     # (n_obs,) mean cache             (weighted mode: m(x) = c + k(x, X) alpha)
+    mean_const: float = 0.0
+
+    @property
+    def weighted(self):
+        return self.mode == "weighted_predictive_covariance"
+
+    @property
+    def posterior(self):
+        """the covariance part is the GP posterior predictive covariance (stacked landmarks [X_nys; X_obs])"""
+        return self.mode in ("predictive_covariance", "weighted_predictive_covariance")
 
     @property
     def stationary(self):
@@ -85,7 +96,7 @@ def _covariance_cache(model):
 def introspect(kernel) -> Optional[KernelSpec]:
     model = getattr(kernel, "model", None)
     mode = getattr(kernel, "mode", None)
-    if model is None or mode not in ("kernel", "predictive_covariance"):
+    if model is None or mode not in ("kernel", "predictive_covariance", "weighted_predictive_covariance"):
         return None
     covar = getattr(model, "covar_module", None)
     if covar is None:
@@ -100,9 +111,20 @@ def introspect(kernel) -> Optional[KernelSpec]:
     if inv_ls is not None and inv_ls.numel() > 1:
         d = int(inv_ls.numel())
     spec = KernelSpec(family, d, inv_ls, outputscale, mode)
-    if mode == "predictive_covariance":
+    if spec.posterior:
         try:
             spec.woodbury, spec.x_obs = _covariance_cache(model)
+        except Exception:
+            return None
+    if spec.weighted:
+        # m(x) cov(x, y) m(y), SOBER/_kernel.py:33-47: linear in the covariance, so the candidates' weights carry m(x_i)
+        # and the basis carries m(z_l); needs the mean cache and a constant mean (predict_mean, SOBER/_gp.py:240-253)
+        try:
+            spec.alpha = model.prediction_strategy.mean_cache.detach().reshape(-1)
+            const = getattr(model.mean_module, "constant", None)
+            if const is None or spec.alpha.numel() != spec.x_obs.shape[0]:
+                return None
+            spec.mean_const = float(torch.as_tensor(const).detach().reshape(-1)[0])
         except Exception:
             return None
     return spec

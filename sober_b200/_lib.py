@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SOBER_B200_LIB") or os.path.join(_HERE, "libsober_b200.so")
 
 OK = 0
+ABI_VERSION = 2   # SOBER_B200_ABI_VERSION of include/sober_b200.h
 _STATUS = {1: "invalid argument", 2: "CUDA error", 3: "unsupported shape/family", 4: "workspace too small"}
 
 RBF, MATERN12, MATERN32, MATERN52, TANIMOTO, TANIMOTO_BITS, HAMMING_LUT = range(7)
@@ -74,6 +75,7 @@ PROTOTYPES = {
     "sober_fp64_probe": (C.c_int, [_I32, _I64, _P, _P]),
     "sober_cholesky_upper_fits": (C.c_int, [_I32]),
     "sober_cholesky_upper": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _P]),
+    "sober_gp_rows": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _D, _P, _D, _D, _D, _D, _P, _P, _P, _P]),
     "sober_kmeans_assign": (C.c_int, [_P, _I64, _I64, _I32, _P, _I32, _P, _P]),
     "sober_partition_stream": (C.c_int, [_I32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "sober_dmma_probe": (C.c_int, [_I32, _I64, _P, _P]),
@@ -104,7 +106,7 @@ def load():
             raise SoberB200Error("sober_b200: %s does not export %s" % (LIB_PATH, name)) from exc
         fn.restype = res
         fn.argtypes = args
-    if lib.sober_abi_version() != 1:
+    if lib.sober_abi_version() != ABI_VERSION:
         raise SoberB200Error("sober_b200: ABI version mismatch")
     _lib = lib
     return lib

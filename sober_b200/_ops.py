@@ -380,6 +380,19 @@ class CudaOps:
         self.launches += 1
         return labels
 
+    def gp_rows(self, k_rows, t_rows, alpha, mean_const, kxx_const, noise, min_var, eta, mean, var, pi):
+        """Per-candidate epilogue of the GP posterior (csrc/predict.cu): mean, clamped variance and the LFI measure."""
+        m, n_obs = k_rows.shape
+        assert k_rows.stride(1) == 1 and (t_rows is None or t_rows.stride(1) == 1) and alpha.is_contiguous()
+        with self._guard():
+            t0 = self._begin("gp_rows")
+            check(self.lib.sober_gp_rows(_ptr(k_rows), k_rows.stride(0), _ptr(t_rows),
+                                         0 if t_rows is None else t_rows.stride(0), _ptr(alpha), m, n_obs,
+                                         float(mean_const), None, float(kxx_const), float(noise), float(min_var),
+                                         float(eta), _ptr(mean), _ptr(var), _ptr(pi), self._stream()), "gp_rows")
+            self._end("gp_rows", t0, 16 * m * n_obs + 24 * m)                  # work = HBM bytes
+        self.launches += 1
+
     def partition_stream(self):
         """Stream confined to all SMs but ``SOBER_B200_RESERVE_SMS`` (default 8), or None when the driver cannot
         partition the device (include/sober_b200.h: sober_partition_stream)."""

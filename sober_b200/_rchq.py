@@ -185,15 +185,19 @@ class Recombiner:
     def _landmarks(self, Z, spec, center, inv_ls):
         """Landmark table over L' = L (+ n_obs) stacked landmarks, and the pieces of the predictive-covariance
         correction (SOBER/_kernel.py:35-53): everything the K1 passes need that does not depend on the basis."""
-        lm = {"table": None, "table_z": None, "k_oz": None, "k_zo_w": None}
+        lm = {"table": None, "table_z": None, "k_oz": None, "k_zo_w": None, "m_z": None, "table_obs": None}
         if spec is not None:
             lm["table_z"] = lm["table"] = self._table(Z, spec, center, inv_ls)
-            if spec.mode == "predictive_covariance":
+            if spec.posterior:
                 x_obs = self.ops.f64(spec.x_obs)
                 w = self.ops.f64(spec.woodbury)
                 lm["k_oz"] = self._gram_T(self._points(x_obs, spec, center, inv_ls), lm["table_z"])   # (n_obs x L)
                 lm["k_zo_w"] = lm["k_oz"].T @ w                                                       # (L x n_obs)
                 lm["table"] = self._table(torch.cat([Z, x_obs], 0), spec, center, inv_ls)
+                if spec.weighted:
+                    # predictive mean at the landmarks, m(z) = c + k(z, X_obs) alpha (SOBER/_gp.py:240-253)
+                    lm["m_z"] = spec.mean_const + lm["k_oz"].T @ self.ops.f64(spec.alpha)
+                    lm["table_obs"] = self._table(x_obs, spec, center, inv_ls)
         return lm
 
     def _basis(self, Z, n_basis, kernel, spec, center, inv_ls, lm):
@@ -208,6 +212,8 @@ class Recombiner:
             gram = self._gram_T(self._points(Z, spec, center, inv_ls), lm["table_z"])        # (L x L)
             if k_zo_w is not None:
                 gram = gram - k_zo_w @ lm["k_oz"]
+            if lm["m_z"] is not None:
+                gram = lm["m_z"].unsqueeze(1) * gram * lm["m_z"].unsqueeze(0)
             gram = 0.5 * (gram + gram.T)
             if o.gate == "cholesky" and o.defer_gate and o.nystrom_qr != "householder":
                 # the gate's L x L Cholesky only decides: it runs beside the range finder, which speculates on "passed"
@@ -224,7 +230,8 @@ class Recombiner:
             gram = kernel(Z, Z)
             gram = _psd.repair(gram, o.gate)
             U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr, rotate=rotate)
-        Uext = U if k_zo_w is None else torch.cat([U, -(U @ k_zo_w)], 1)
+        Um = U if lm["m_z"] is None else U * lm["m_z"].unsqueeze(0)       # weighted mode: the basis carries m(z_l)
+        Uext = Um if k_zo_w is None else torch.cat([Um, -(Um @ k_zo_w)], 1)
         return U, Uext.contiguous()
 
     def _nystrom(self, Z, n_basis, kernel, spec, center, inv_ls):
@@ -331,18 +338,40 @@ class Recombiner:
         obj = None if calc_obj is None else (-1 * calc_obj(pts_rec.to(dev))).to(torch.float64)
         clock.lap("compact+records")
 
+        # weighted mode (SOBER/_kernel.py:33-47): predictive mean of every local candidate, once
+        m_x = None
+        if spec is not None and spec.weighted:
+            alpha = ops.f64(spec.alpha)
+            m_x = torch.empty(n_rows, dtype=torch.float64, device=dev)
+            for c0 in range(0, n_rows, 1 << 17):
+                rows = self._gram_T(self._points(X[c0:c0 + (1 << 17)], spec, center, inv_ls), lm["table_obs"])
+                m_x[c0:c0 + (1 << 17)] = spec.mean_const + rows @ alpha
+        self._m_x = m_x
+
         def k1_pass(alive, n_local, pos0, remaining):
             """Grouped kernel-column sums of one iteration: At, totw and the second count of the remainder."""
             ES = (remaining // S) * S
-            at, totw = self._accumulate(st, alive, n_local, pos0, ES, S)
-            Lp = at.shape[1]
             t0 = min(max(ES - pos0, 0), n_local)           # first local offset belonging to the remainder
+            src = alive
+            if m_x is not None:
+                # the kernel columns are weighted with mu_i m(x_i); the group MASSES stay sums of mu_i
+                wts = alive.mass * m_x[alive.idx.long()]
+                if alive.rec is not None:
+                    alive.rec[:, d + 1] = wts
+                src = Alive(alive.idx, wts, alive.rec)
+            at, totw = self._accumulate(st, src, n_local, pos0, ES, S)
+            if m_x is not None:
+                lead = pos0 % S
+                padded = torch.zeros(-(-(lead + t0) // S) * S, dtype=torch.float64, device=dev)
+                padded[lead:lead + t0] = alive.mass[:t0]
+                totw = padded.reshape(-1, S).sum(0)
+            Lp = at.shape[1]
             extra = torch.zeros(Lp + 3, dtype=torch.float64, device=dev)
             if t0 < n_local:
                 # second count of the remainder into the last group (SOBER/_rchq.py:153-164)
-                tail_at, tail_tw = self._accumulate(st, alive.tail(t0), n_local - t0, 0, n_local - t0, 1)
+                tail_at, tail_tw = self._accumulate(st, src.tail(t0), n_local - t0, 0, n_local - t0, 1)
                 extra[:Lp] = tail_at[0]
-                extra[Lp] = tail_tw[0]
+                extra[Lp] = tail_tw[0] if m_x is None else alive.mass[t0:].sum()
             return at, totw, extra, t0
 
         # The first (and by far the longest) K1 pass does not depend on the Nystrom basis: it runs on a stream confined
@@ -496,6 +525,13 @@ class Recombiner:
             comm.all_reduce(feats_t)
             comm.all_reduce(all_mass)
             comm.all_reduce(all_idx)
+        if getattr(self, "_m_x", None) is not None:
+            # weighted mode: feature rows carry m(x_i) (the basis already carries m(z_l))
+            all_m = torch.zeros(remaining, dtype=torch.float64, device=dev)
+            all_m[pos0:pos0 + n_local] = self._m_x[idx.long()]
+            if comm.world > 1:
+                comm.all_reduce(all_m)
+            feats_t = feats_t * all_m.unsqueeze(1)
         feats = feats_t @ UextT                                                            # (R x n)
         head_obj = None
         if obj is not None:

@@ -117,12 +117,15 @@ __device__ __forceinline__ unsigned long long cp_pack(double ratio, int row) {
 constexpr int CP_B = 8;           // register block: columns of the panel a row thread holds in registers
 constexpr int CP_HB = CP_HDR + CP_B;
 
-// Roles inside a CTA:  warp 0 = PIVOT warp (holds all rows of the CTA's block in registers, lane l rows l, l + 32, ...:
-// ratio test, warp-level argmin, the post and the register update never leave the warp -- no block barrier inside a
-// step);  warp 1 = HELPER (follows every exchange: records the multipliers L and the pivots, and -- in the CTA that owns
-// the pivot row -- sends that row's entries right of the block to everybody);  warps 2..7 sleep at the block-end barrier
-// and join for the rank-8 update of the rest of the panel.
-template <int RPL>
+// Roles inside a CTA:  warps 0 .. NPW-1 = PIVOT warps (together they hold all rows of the CTA's block in registers, at
+// most two rows per lane: ratio test, argmin and register update stay inside the warp; with NPW > 1 the warps' best
+// rows meet in shared memory behind a named barrier of the pivot warps only);  warp 7 = HELPER (follows every
+// exchange: records the multipliers L and the pivots, and -- in the CTA that owns the pivot row -- sends that row's
+// entries right of the block to everybody);  the other warps sleep at the block-end barrier and join for the rank-8
+// update of the rest of the panel.
+constexpr int CP_HELPER = CP_THREADS / 32 - 1;
+
+template <int RPL, int NPW>
 __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanelParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     constexpr int P = CP_P, B = CP_B, HB = CP_HB;
@@ -133,15 +136,17 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
     const int ri = t & (tr - 1), ci = t / tr;     // mapping of the block-end update: row ri, columns ci, ci + tc, ...
     const int row0 = r * p.rpc;
     const int nrows = max(0, min(p.rpc, S - row0));
+    const bool pivot = warp < NPW, helper = warp == CP_HELPER;
 
     extern __shared__ __align__(16) double sm[];
     double* panel = sm;                            // [nb][rpcp]   column-major panel (u columns once a block is done)
     double* recv = panel + (size_t)nb * rpcp;      // [2][P][HB]   candidates of the current / next step
     double* gbuf = recv + 2 * P * HB;              // [nb][B]      raw pivot rows of the block, then R (transposed)
     double* lblk = gbuf + (size_t)nb * B;          // [B][B]       in-block multipliers L[q][q']
-    double* stage = lblk + B * B;                  // [HB]         this CTA's candidate (header + block row)
+    double* stage = lblk + B * B;                  // [2][4][HB]   per exchange parity and pivot warp: its best row
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ __align__(8) uint64_t gbar;
+    __shared__ unsigned long long red_key[2][4];
     __shared__ int jblk_s[B];
     __shared__ volatile int helper_read;           // exchanges whose buffer the helper has finished reading
     __shared__ volatile int stop_s;
@@ -163,13 +168,15 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
         const int c = e / rpcp, i = e - c * rpcp;
         panel[e] = i < nrows ? p.basis[(size_t)(p.t0 + c) * S + row0 + i] : 0.0;
     }
+    // rows of this lane: (warp * RPL + m) * 32 + lane
     double mu[RPL];
     bool ok[RPL];
+    int rowi[RPL];
 #pragma unroll
     for (int m = 0; m < RPL; ++m) {
-        const int i = lane + 32 * m;
-        ok[m] = warp == 0 && i < nrows;
-        mu[m] = ok[m] ? p.mu[row0 + i] : 0.0;
+        rowi[m] = (warp * RPL + m) * 32 + lane;
+        ok[m] = pivot && rowi[m] < nrows;
+        mu[m] = ok[m] ? p.mu[row0 + rowi[m]] : 0.0;
     }
     __syncthreads();
     cluster.sync();                                // every CTA's barriers are initialised before anybody posts
@@ -184,9 +191,9 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
         pt = now_;                        \
     }
 
-    double blk[RPL][B];                            // pivot warp: this lane's rows of the current block
-    // Pivot warp: ratio test on block column qc (registers), warp argmin, post of this CTA's candidate for pivot
-    // column e to all CTAs.
+    double blk[RPL][B];                            // pivot warps: this lane's rows of the current block
+    // Pivot warps: ratio test on block column qc (registers), argmin over the CTA's rows, post of the CTA's candidate
+    // for pivot column e to all CTAs.
     auto test_and_post = [&](int e, int qc) {
         const int par = e & 1;
         unsigned long long key = CP_NONE;
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
                 double y;
                 asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
                 y = fma(y, fma(-v, y, 1.0), y);
-                const unsigned long long kq = cp_pack(mu[m] * y, lane + 32 * m);
+                const unsigned long long kq = cp_pack(mu[m] * y, rowi[m]);
                 if (kq < key) { key = kq; balpha = mu[m]; binv = v; }
             }
         }
@@ -217,46 +224,58 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
         const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
         const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
         key = ((unsigned long long)mhi << 32) | mlo;
-        const bool have = key != CP_NONE;
-        const int bi = (int)(key & ((1ull << CP_IDX_BITS) - 1));
-        const int mstar = bi >> 5;                 // uniform: which of its rows the winning lane stages
-        if (have && mine == key) {
-            stage[0] = balpha; stage[1] = binv; stage[2] = (double)(row0 + bi); stage[3] = 0.0;
-        }
-        if (have) {
+        double* st = stage + (size_t)(par * 4 + warp) * HB;
+        if (key != CP_NONE) {
+            const int bi = (int)(key & ((1ull << CP_IDX_BITS) - 1));
+            const int mstar = (bi >> 5) - warp * RPL;          // uniform: which of its rows the warp's best lane stages
+            if (mine == key) {
+                st[0] = balpha; st[1] = binv; st[2] = (double)(row0 + bi); st[3] = 0.0;
+            }
 #pragma unroll
             for (int m = 0; m < RPL; ++m)
                 if (m == mstar && mine == key) {
 #pragma unroll
-                    for (int q = 0; q < B; ++q) stage[CP_HDR + q] = blk[m][q];
+                    for (int q = 0; q < B; ++q) st[CP_HDR + q] = blk[m][q];
                 }
         }
+        int wsel = warp;
+        if (NPW > 1) {
+            if (lane == 0) red_key[par][warp] = key;
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * NPW) : "memory");   // the pivot warps only
+#pragma unroll
+            for (int w = NPW - 1; w >= 0; --w) {
+                const unsigned long long kw = red_key[par][w];
+                if (kw <= key) { key = kw; wsel = w; }
+            }
+        } else {
+            __syncwarp();
+        }
+        const bool have = key != CP_NONE;
+        const double* win = stage + (size_t)(par * 4 + wsel) * HB;
         while (helper_read < e) {
         }
-        __syncwarp();
-        for (int ch = lane; ch < P * (HB / 2); ch += 32) {
-            const int peer = ch / (HB / 2), part = ch - peer * (HB / 2);
-            double a = have ? stage[2 * part] : 0.0, b = have ? stage[2 * part + 1] : 0.0;
+        // pivot warp w posts to the CTAs p with p mod NPW == w: 6 16-byte chunks each
+        constexpr int CH = (P / NPW) * (HB / 2);
+        for (int ch = lane; ch < CH; ch += 32) {
+            const int pl = ch / (HB / 2), part = ch - pl * (HB / 2);
+            const int peer = pl * NPW + warp;
+            double a = have ? win[2 * part] : 0.0, b = have ? win[2 * part + 1] : 0.0;
             if (part == 1 && !have) a = -1.0;      // header[2] = row index, -1: no candidate
             const uint32_t dst = cp_mapa(smem_addr(recv + (size_t)(par * P + r) * HB), (uint32_t)peer);
             const uint32_t bar = cp_mapa(smem_addr(&bars[par]), (uint32_t)peer);
             cp_st_async2(dst + (uint32_t)part * 16u, a, b, bar);
         }
-        __syncwarp();                              // the stage may be rewritten by the next call
     };
     // winner of the 8 candidates of exchange s: lowest ratio, then lowest CTA rank (= lowest row); -1: none
     auto winner = [&](const double* rb, double& alpha) {
         double al[P];
-        bool va[P];
+        int wi[P];
 #pragma unroll
         for (int c = 0; c < P; ++c) {
             const double2 h = *reinterpret_cast<const double2*>(rb + (size_t)c * HB);
             al[c] = h.x;
-            va[c] = rb[(size_t)c * HB + 2] >= 0.0;
+            wi[c] = rb[(size_t)c * HB + 2] >= 0.0 ? c : -1;
         }
-        int wi[P];
-#pragma unroll
-        for (int c = 0; c < P; ++c) wi[c] = va[c] ? c : -1;
 #pragma unroll
         for (int w = 1; w < P; w *= 2)
 #pragma unroll
@@ -274,17 +293,17 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
     for (int b0 = 0; b0 < nb; b0 += B) {
         const int bw = min(B, nb - b0);
         const int glen = nb - (b0 + bw);           // columns of the panel to the right of this block
-        if (warp == 0) {
+        if (pivot) {
 #pragma unroll
             for (int m = 0; m < RPL; ++m)
 #pragma unroll
                 for (int q = 0; q < B; ++q)
-                    blk[m][q] = (ok[m] && q < bw) ? panel[(size_t)(b0 + q) * rpcp + lane + 32 * m] : 0.0;
-            if (lane == 0 && glen > 0) mbar_expect_tx(&gbar, (uint32_t)(bw * glen * 8));
+                    blk[m][q] = (ok[m] && q < bw) ? panel[(size_t)(b0 + q) * rpcp + rowi[m]] : 0.0;
+            if (t == 0 && glen > 0) mbar_expect_tx(&gbar, (uint32_t)(bw * glen * 8));
             test_and_post(b0, 0);
             CP_TICK(4)
         }
-        if (warp <= 1) {
+        if (pivot || helper) {
 #pragma unroll
             for (int q = 0; q < B; ++q) {
                 if (q < bw && !stopped) {
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
                         const double inv = wb[1];
                         const int jg = (int)wb[2];
                         done = s + 1;
-                        if (warp == 0) {
+                        if (pivot) {
                             double rowv[B];
 #pragma unroll
                             for (int qq = 0; qq < B; qq += 2) {
@@ -309,11 +328,11 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
                                 rowv[qq] = v2.x;
                                 rowv[qq + 1] = v2.y;
                             }
-                            if (lane == 0 && s + 2 < nb) mbar_expect_tx(&bars[par], XBYTES);
+                            if (t == 0 && s + 2 < nb) mbar_expect_tx(&bars[par], XBYTES);
 #pragma unroll
                             for (int m = 0; m < RPL; ++m) {
                                 const double v = blk[m][q];
-                                const bool pv = ok[m] && (row0 + lane + 32 * m == jg);
+                                const bool pv = ok[m] && (row0 + rowi[m] == jg);
                                 const double u = pv ? 1.0 : v * inv;
                                 blk[m][q] = u;
                                 mu[m] = pv ? 0.0 : fma(-alpha, v, mu[m]);
@@ -347,9 +366,9 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
                     }
                 }
             }
-            if (warp == 1 && stopped && lane == 0) helper_read = nb + 1;
-            if (warp == 0) {
-                if (stopped && lane == 0) stop_s = 1;
+            if (helper && stopped && lane == 0) helper_read = nb + 1;
+            if (pivot) {
+                if (stopped && t == 0) stop_s = 1;
                 // u columns of the block -> panel (U of the trailing update, L rows, multipliers of the rank-8 update)
                 if (!stopped) {
 #pragma unroll
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
                         if (ok[m]) {
 #pragma unroll
                             for (int q = 0; q < B; ++q)
-                                if (q < bw) panel[(size_t)(b0 + q) * rpcp + lane + 32 * m] = blk[m][q];
+                                if (q < bw) panel[(size_t)(b0 + q) * rpcp + rowi[m]] = blk[m][q];
                         }
                 }
                 CP_TICK(3)
@@ -367,7 +386,7 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
         if (stop_s) break;
         if (glen > 0) mbar_wait(&gbar, (uint32_t)((b0 / B) & 1));
         CP_TICK(5)
-        if (p.write_u && warp == CP_THREADS / 32 - 1) {
+        if (p.write_u && helper) {
             // rows of L for the trailing-column solve, written by the CTA that owns the pivot row
             for (int q = 0; q < bw; ++q) {
                 const int jg = jblk_s[q];
@@ -423,10 +442,10 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
 #undef CP_TICK
     __syncthreads();
     const bool stopped_all = stop_s != 0;
-    if (warp == 0) {
+    if (pivot) {
 #pragma unroll
         for (int m = 0; m < RPL; ++m)
-            if (ok[m]) p.mu[row0 + lane + 32 * m] = mu[m];
+            if (ok[m]) p.mu[row0 + rowi[m]] = mu[m];
     }
     if (p.write_u && !stopped_all) {
         for (int e = t; e < nb * rpcp; e += CP_THREADS) {
@@ -548,18 +567,19 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
 }
 
 struct PanelPlan {
-    int rpl, rpc, rpcp, tr, nb;
+    int rpl, npw, rpc, rpcp, tr, nb;
     bool single;
     size_t smem(int nb_) const {
-        return ((size_t)nb_ * rpcp + 2 * (size_t)CP_P * CP_HB + (size_t)nb_ * CP_B + CP_B * CP_B + CP_HB) * 8;
+        return ((size_t)nb_ * rpcp + 2 * (size_t)CP_P * CP_HB + (size_t)nb_ * CP_B + CP_B * CP_B + 2 * 4 * CP_HB) * 8;
     }
 };
 
 static bool plan_panel(int S, int k, int nb_hint, PanelPlan* pl) {
     if (S <= 0 || k <= 0 || k >= S + 1) return false;
     pl->rpc = (S + CP_P - 1) / CP_P;
-    if (pl->rpc > CP_THREADS) return false;             // S <= 2048: the pivot warp holds 8 rows per lane at most
-    pl->rpl = pl->rpc <= 32 ? 1 : (pl->rpc <= 64 ? 2 : (pl->rpc <= 128 ? 4 : 8));
+    if (pl->rpc > CP_THREADS) return false;             // S <= 2048: four pivot warps, two rows per lane
+    pl->rpl = pl->rpc <= 32 ? 1 : 2;
+    pl->npw = pl->rpc <= 64 ? 1 : (pl->rpc <= 128 ? 2 : 4);
     int tr = 32;
     while (tr < pl->rpc && tr < CP_THREADS) tr *= 2;
     pl->tr = tr;
@@ -607,10 +627,10 @@ extern "C" int sober_car_panel_profiled(double* basis, int32_t k, int32_t S, dou
     double* Rt = lmat + CP_NB * CP_NB;
     SOBER_CUDA_CHECK(cudaMemsetAsync(state, 0, 16, st));
 
-    void (*kern)(const CarPanelParams) = pl.rpl == 1 ? car_panel_kernel<1>
-                                         : (pl.rpl == 2 ? car_panel_kernel<2>
-                                                        : (pl.rpl == 4 ? car_panel_kernel<4> : car_panel_kernel<8>));
-    const int kvar = pl.rpl == 1 ? 0 : (pl.rpl == 2 ? 1 : (pl.rpl == 4 ? 2 : 3));
+    void (*kern)(const CarPanelParams) = pl.rpl == 1 ? car_panel_kernel<1, 1>
+                                         : (pl.npw == 1 ? car_panel_kernel<2, 1>
+                                                        : (pl.npw == 2 ? car_panel_kernel<2, 2> : car_panel_kernel<2, 4>));
+    const int kvar = pl.rpl == 1 ? 0 : (pl.npw == 1 ? 1 : (pl.npw == 2 ? 2 : 3));
     const size_t smem_max = pl.smem(pl.single ? k : pl.nb);
     {   // the > 48 KB opt-in is per device and sticky: once per (device, kernel variant), never inside a graph capture
         static int configured[64][4] = {};

@@ -9,7 +9,7 @@ from oracle import rchq as oracle_rchq
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["matern6d_rest", "matern6d_pow2", "rbf2d_branin", "rbf_ard5d", "ising24_hamming", "tanimoto256",
-         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d"]
+         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d", "wpredcov_matern6d"]
 LOOP_CASES = [c for c in CASES if c not in ("direct_branch", "tiny_passthrough")]
 
 
@@ -37,6 +37,7 @@ class Case:
         self.n_car = int(z["n_car"])
         self.Xobs = t("Xobs") if "Xobs" in z else None
         self.noise = float(z["noise"]) if "noise" in z else None
+        self.yobs = t("yobs") if "yobs" in z else None
         self._t = t
 
     def car(self, i, key):
@@ -46,7 +47,7 @@ class Case:
         cov = ok.make_kernel(self.fam, self.ls if self.ls is not None else 1.0, self.os).to(self.device)
         if self.mode == "kernel":
             return ok.Kernel(ok.BareModel(cov), mode="kernel")
-        return ok.Kernel(ok.GPModel(cov, self.Xobs, None, noise=self.noise), mode=self.mode)
+        return ok.Kernel(ok.GPModel(cov, self.Xobs, self.yobs, noise=self.noise), mode=self.mode)
 
 
 # the fast mode's null-space basis restated with LAPACK (one definition, shared with bench.py's parity block)

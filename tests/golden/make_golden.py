@@ -164,6 +164,13 @@ def case_inputs(name):
         Xo = torch.rand(30, 6, dtype=f64, generator=g)
         return dict(X=X, Z=Z, mu=_weights(3072, 0, g), b=24, fam="matern", ls=[0.6], os=1.0,
                     mode="predictive_covariance", Xobs=Xo, noise=1e-2)
+    if name == "wpredcov_matern6d":      # Kernel(model, "weighted_predictive_covariance"): m(x) cov(x, y) m(y), SOBER/_kernel.py:33-47
+        X = torch.rand(3072, 6, dtype=f64, generator=g)
+        Z = X[torch.randperm(3072, generator=g)[:96]].clone()
+        Xo = torch.rand(30, 6, dtype=f64, generator=g)
+        yo = 1.5 + torch.sin(3.0 * Xo).sum(-1) + 0.05 * torch.randn(30, dtype=f64, generator=g)
+        return dict(X=X, Z=Z, mu=_weights(3072, 0, g), b=24, fam="matern", ls=[0.6], os=1.0,
+                    mode="weighted_predictive_covariance", Xobs=Xo, yobs=yo, noise=1e-2)
     if name == "direct_branch":          # n+1 < N <= 2(n+1): a single CAR on the points themselves
         X = torch.rand(40, 3, dtype=f64, generator=g)
         Z = X[:30].clone()
@@ -181,14 +188,14 @@ def case_inputs(name):
 
 
 CASES = ["matern6d_rest", "matern6d_pow2", "rbf2d_branin", "rbf_ard5d", "ising24_hamming", "tanimoto256",
-         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d"]
+         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d", "wpredcov_matern6d"]
 
 
 def build_kernel(spec):
     cov = ok.make_kernel(spec["fam"], spec["ls"] if spec["ls"] is not None else 1.0, spec["os"])
     if spec["mode"] == "kernel":
         return ok.Kernel(ok.BareModel(cov), mode="kernel")
-    model = ok.GPModel(cov, spec["Xobs"], None, noise=spec["noise"])
+    model = ok.GPModel(cov, spec["Xobs"], spec.get("yobs"), noise=spec["noise"])
     return ok.Kernel(model, mode=spec["mode"])
 
 
@@ -218,7 +225,7 @@ def main():
     ref_t = drug.batch_tanimoto_sim(a, b).clamp_min(0)
     assert torch.equal(ref_t, ok.TanimotoKernel().forward(a, b)), "Tanimoto restatement differs from reference"
 
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):       # optional: regenerate only the named fixtures
         spec = case_inputs(name)
         idx, w, mu_after, stages, kernel = run_reference(rchq, spec)
         out = {"X": spec["X"].numpy() if spec["fam"] != "tanimoto" and name != "ising24_hamming"
@@ -236,6 +243,8 @@ def main():
         if "Xobs" in spec:
             out["Xobs"] = spec["Xobs"].numpy()
             out["noise"] = np.float64(spec["noise"])
+        if "yobs" in spec:
+            out["yobs"] = spec["yobs"].numpy()
         n_car = 0
         for stage, payload in stages:
             if stage == "basis":

@@ -35,7 +35,7 @@ def test_header_symbols_all_exported(built):
 
 def test_python_prototypes_cover_header(built):
     assert set(declared_symbols()) == set(built.PROTOTYPES)
-    assert built.load().sober_abi_version() == 1
+    assert built.load().sober_abi_version() == built.ABI_VERSION == 2
 
 
 def test_header_is_plain_c():
@@ -75,3 +75,13 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_integration_doc_struct_matches_binding(built):
+    """The ctypes struct printed in INTEGRATION.md is what a host would copy: same fields, same order as _lib.GroupArgs
+    (a short struct would make the library read past it), and the ABI version it asserts is the current one."""
+    doc = open(os.path.join(os.path.dirname(HEADER), "..", "INTEGRATION.md")).read()
+    block = doc.split("class GroupArgs(C.Structure)")[1].split("]\n")[0]
+    fields = re.findall(r'\("([a-zA-Z_0-9]+)",\s*C\.c_[a-z0-9_]+\)', block)
+    assert fields == [name for name, _ in built.GroupArgs._fields_]
+    assert "sober_abi_version() == %d" % built.ABI_VERSION in doc

@@ -8,7 +8,8 @@ import types
 import pytest
 
 import sober_b200
-from sober_b200._rchq import recombination as fast
+from sober_b200._rchq import recombination as device_fast
+from sober_b200._install import _fast as fast          # what install() binds: same call, results on the caller's device
 
 
 def _fake_tree(pkg):
@@ -49,6 +50,7 @@ def test_signature_matches_reference_source():
     """Same parameter names, order and defaults as SOBER/_rchq.py:5-14."""
     import inspect
     sig = inspect.signature(fast)
+    assert str(sig) == str(inspect.signature(device_fast))
     assert list(sig.parameters) == ["pts_rec", "pts_nys", "num_pts", "kernel", "device", "dtype", "init_weights",
                                     "calc_obj"]
     assert sig.parameters["init_weights"].default is None and sig.parameters["calc_obj"].default is None

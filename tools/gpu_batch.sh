@@ -18,6 +18,10 @@ for step in "$@"; do
     ncusmoke) TMO=600 TAILN=60 run ncu_smoke ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_smoke.csv python -c "import __graft_entry__ as g; g.smoke()" ;;
     parbrk)   TAILN=20 run parity_breakdown python tools/parity_breakdown.py ;;
     ncucar)   TMO=600 TAILN=5 run ncu_car ncu --metrics gpu__time_duration.sum --clock-control none -k regex:car_panel -c 400 --csv --log-file $OUT/launches_car.csv python tools/time_car.py ;;
+    shard2)   TMO=600 run sharded_tests python -m pytest tests/test_gpu_sharded.py -x -q -m gpu ;;
+    mbench2)  TMO=900 TAILN=3 run bench_2gpu python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 ;;
+    mbench4)  TMO=900 TAILN=3 run bench_4gpu python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 5 --warmup 3 ;;
+    mbench8)  TMO=900 TAILN=3 run bench_8gpu python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 5 --warmup 3 ;;
     stagepar) TAILN=25 run stage_c2_parity python tools/stage_breakdown.py c2 parity ;;
     bench2)   TMO=600 TAILN=3 run bench_c2 python bench.py --steps 10 --warmup 3 ;;
     bench5)   TMO=600 TAILN=3 run bench_c5 python bench.py --workload c5 --steps 5 --warmup 2 --no-cpu-baseline ;;
