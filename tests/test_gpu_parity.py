@@ -123,6 +123,8 @@ def test_group_accumulate_matches_oracle_trace(ops, cuda_device, name, variant):
     case = Case(name)                                   # oracle on the CPU
     if case.objective is not None:
         pytest.skip("objective branch covered end-to-end")
+    if case.mode == "weighted_predictive_covariance":
+        pytest.skip("the K1 weights carry m(x) inside Recombiner.run: covered end-to-end")
     groups, updates = [], []
 
     def trace(stage, payload):
