@@ -520,10 +520,19 @@ def main():
         else:
             one = Runner("c5", dev, 0, 1)
             ksteps = max(2, min(5, args.steps // 2))
-            ms, _, _ = one.timed(ksteps, 2, flush)
+            ms, _, _ = one.timed(ksteps, 2, flush, ops)
+            t5 = ops.timing_summary()
+            uc5, k15 = ops.timing_largest("update_compact"), ops.timing_largest("group_accumulate")
+            ops.timing = None
             extras["c5"] = {"workload": WORKLOADS["c5"][6], "n_rec_total": one.n_total, "ms_per_step": ms / ksteps,
                             "steps": ksteps, "value": one.n_total * ksteps / (ms * 1e-3), "unit": "candidates/s",
-                            "note": "the north_star target config (BASELINE configs[4]) on this one GPU"}
+                            "note": "the north_star target config (BASELINE configs[4]) on this one GPU",
+                            "stage_ms_per_step": {k: v[1] / ksteps for k, v in t5.items()},
+                            # the streaming pass over all 1e7 candidates (weight update + compaction + record move)
+                            "update_compact_largest": {"ms": uc5[0], "bytes": uc5[1],
+                                                       "GB/s": uc5[1] / (uc5[0] * 1e-3) / 1e9} if uc5 else None,
+                            "k1_largest": {"ms": k15[0], "pairs": k15[1],
+                                           "tflops_at_26_flop_per_pair": k15[1] * 26 / (k15[0] * 1e-3) / 1e12} if k15 else None}
             del one
         torch.cuda.empty_cache()
 

@@ -18,9 +18,11 @@ def predict(test_x, model):
     root = model.prediction_strategy.covar_cache
     k_xo = model.covar_module.forward(test_x, x_obs)
     mean = model.mean_module.constant + k_xo @ model.prediction_strategy.mean_cache
-    prior_var = torch.diagonal(model.covar_module.forward(test_x, test_x)) if len(test_x) <= 4096 else \
-        torch.cat([torch.diagonal(model.covar_module.forward(test_x[s:s + 4096], test_x[s:s + 4096]))
-                   for s in range(0, len(test_x), 4096)])
+    if test_x.dim() == 2 and len(test_x) > 4096:        # the diagonal only: chunked so that nothing N x N is formed
+        prior_var = torch.cat([torch.diagonal(model.covar_module.forward(test_x[s:s + 4096], test_x[s:s + 4096]))
+                               for s in range(0, len(test_x), 4096)])
+    else:                                                # (batch, S, d) inputs: one diagonal per batch entry
+        prior_var = torch.diagonal(model.covar_module.forward(test_x, test_x), dim1=-2, dim2=-1)
     var = prior_var - ((k_xo @ root) ** 2).sum(-1) + model.likelihood.noise
     return mean, var.clamp_min(MIN_VARIANCE)
 

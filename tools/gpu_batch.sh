@@ -22,6 +22,7 @@ for step in "$@"; do
     mbench2)  TMO=900 TAILN=3 run bench_2gpu python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 ;;
     mbench4)  TMO=900 TAILN=3 run bench_4gpu python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 5 --warmup 3 ;;
     mbench8)  TMO=900 TAILN=3 run bench_8gpu python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 5 --warmup 3 ;;
+    projbrk)  TAILN=30 run projector_breakdown python tools/projector_breakdown.py ;;
     stagepar) TAILN=25 run stage_c2_parity python tools/stage_breakdown.py c2 parity ;;
     bench2)   TMO=600 TAILN=3 run bench_c2 python bench.py --steps 10 --warmup 3 ;;
     bench5)   TMO=600 TAILN=3 run bench_c5 python bench.py --workload c5 --steps 5 --warmup 2 --no-cpu-baseline ;;
