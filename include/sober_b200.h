@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define SOBER_B200_ABI_VERSION 2   /* 2: car_panel, gp_rows, popc_probe added; sober_group_args unchanged since 1 */
+#define SOBER_B200_ABI_VERSION 2   /* 2: car_panel, gp_rows, popc_probe added; sober_group_args grew kx / ldkx / aw / n_obs / transform at its end */
 
 enum sober_status {
     SOBER_OK = 0,
@@ -139,6 +139,14 @@ typedef struct sober_group_args {
     const double* rec;    /* record layout (sober_make_records), row j = local position j; NULL = indexed layout */
     int64_t ldr;
     const double* lut;    /* SOBER_HAMMING_LUT: d + 1 kernel values indexed by the Hamming distance */
+    /* Non-linear posterior mode (indexed layout only; all NULL / 0 otherwise) -- SOBER/BASQ/_scale_mmlt.py:256-275:
+     *   At[g, l] = sum k_post(z_l, x) mu,  k_post = expm1( outputscale * k(z_l, x) - <aw[l, :], kx[row(x), :]> )
+     * kx: (N x n_obs, ldkx) rows k(x, X_obs) addressed by row id like X;  aw: (L x n_obs) rows k(z_l, X_obs) W. */
+    const double* kx;
+    int64_t ldkx;
+    const double* aw;
+    int32_t n_obs;
+    int32_t transform;    /* reserved: 1 = expm1 */
 } sober_group_args;
 
 int64_t sober_group_accumulate_workspace(const sober_group_args* args);

@@ -29,6 +29,12 @@ class KernelSpec:
     woodbury: Optional[torch.Tensor] = None  # (n_obs, n_obs)  S S^T           (SOBER/_gp.py:255-278)
     alpha: Optional[torch.Tensor] = None     # (n_obs,) mean cache             (weighted mode: m(x) = c + k(x, X) alpha)
     mean_const: float = 0.0
+    noise: float = 0.0                       # gspace mode: likelihood noise (enters the predictive variance)
+    jitter: float = 0.0                      # gspace mode: ScaleMmltGP.jitter
+
+    @property
+    def gspace(self):
+        return self.mode == "gspace"
 
     @property
     def weighted(self):
@@ -37,7 +43,7 @@ class KernelSpec:
     @property
     def posterior(self):
         """the covariance part is the GP posterior predictive covariance (stacked landmarks [X_nys; X_obs])"""
-        return self.mode in ("predictive_covariance", "weighted_predictive_covariance")
+        return self.mode in ("predictive_covariance", "weighted_predictive_covariance", "gspace")
 
     @property
     def stationary(self):
@@ -93,7 +99,32 @@ def _covariance_cache(model):
     return root @ root.T, x_obs.detach()
 
 
+def _introspect_gspace(kernel) -> Optional[KernelSpec]:
+    """``ScaleMmltGP.gspace_kernel`` (SOBER/BASQ/_scale_mmlt.py:256-275), the bound method BASQ.quadrature hands to
+    ``recombination`` (SOBER/BASQ/_basq.py:55-67):  mu_g(x) mu_g(y) (exp(cov_h(x, y)) - 1)  with the h-space GP
+    ``owner.model``.  Non-linear in the covariance: served by the POST mode of K1 (csrc/group_accumulate.cu)."""
+    owner = getattr(kernel, "__self__", None)
+    if owner is None or getattr(kernel, "__name__", "") != "gspace_kernel" or not hasattr(owner, "model"):
+        return None
+    from ._predict import describe_gp
+    gp = describe_gp(owner.model)
+    if gp is None:
+        return None
+    spec = gp.kernel
+    spec.mode = "gspace"
+    spec.x_obs, spec.woodbury, spec.alpha = gp.x_obs, gp.woodbury, gp.alpha
+    spec.mean_const, spec.noise = gp.mean_const, gp.noise
+    try:
+        spec.jitter = float(torch.as_tensor(getattr(owner, "jitter", 0.0)).reshape(-1)[0])
+    except Exception:
+        return None
+    return spec
+
+
 def introspect(kernel) -> Optional[KernelSpec]:
+    gs = _introspect_gspace(kernel)
+    if gs is not None:
+        return gs
     model = getattr(kernel, "model", None)
     mode = getattr(kernel, "mode", None)
     if model is None or mode not in ("kernel", "predictive_covariance", "weighted_predictive_covariance"):

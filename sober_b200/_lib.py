@@ -36,6 +36,7 @@ class GroupArgs(C.Structure):
         ("variant", C.c_int32), ("unit_weights", C.c_int32),
         ("rec", C.c_void_p), ("ldr", C.c_int64),
         ("lut", C.c_void_p),
+        ("kx", C.c_void_p), ("ldkx", C.c_int64), ("aw", C.c_void_p), ("n_obs", C.c_int32), ("transform", C.c_int32),
     ]
 
 

@@ -197,7 +197,8 @@ class CudaOps:
         return idx[:r], out[:r], r
 
     # -- K1 ------------------------------------------------------------------------------------------------
-    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None, rec=None, unit_weights=False):
+    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None, rec=None, unit_weights=False,
+                         post=None):
         """At (S x L) and totw (S) for the positions [pos0, pos0 + n_local) this device owns.  ``rec``: record rows of
         exactly those positions (record layout); otherwise ``pts`` + ``idx`` + ``mu`` (indexed layout)."""
         if int(n_local) == 0:
@@ -222,6 +223,11 @@ class CudaOps:
         a.outputscale = lm.outputscale
         a.Zt, a.zn = lm.zt.data_ptr(), lm.zn.data_ptr()
         a.lut = None if lm.lut is None else lm.lut.data_ptr()
+        if post is not None:
+            # non-linear posterior mode: kx (N x n_obs) rows k(x, X_obs) by row id, aw (L x n_obs) rows k(z_l, X_obs) W
+            kx, aw = post
+            assert rec is None and kx.stride(1) == 1 and aw.is_contiguous() and aw.shape == (lm.L, kx.shape[1])
+            a.kx, a.ldkx, a.aw, a.n_obs, a.transform = kx.data_ptr(), kx.stride(0), aw.data_ptr(), kx.shape[1], 1
         a.At, a.totw = At.data_ptr(), totw.data_ptr()
         a.variant = self.variant
         nbytes = self.lib.sober_group_accumulate_workspace(C.byref(a))

@@ -163,7 +163,8 @@ class Recombiner:
         return LandmarkTable(pts.contiguous(), (pts * pts).sum(-1).contiguous(), spec.family, spec.outputscale)
 
     def _use_records(self, spec, d):
-        return spec is not None and d <= _lib.RECORD_MAX_D and self.opts.k1_variant != 1
+        return (spec is not None and d <= _lib.RECORD_MAX_D and self.opts.k1_variant != 1
+                and not getattr(spec, "gspace", False))          # the POST mode of K1 reads the indexed layout
 
     def _points(self, X, spec, center, inv_ls):
         if self._bits:
@@ -193,11 +194,16 @@ class Recombiner:
                 w = self.ops.f64(spec.woodbury)
                 lm["k_oz"] = self._gram_T(self._points(x_obs, spec, center, inv_ls), lm["table_z"])   # (n_obs x L)
                 lm["k_zo_w"] = lm["k_oz"].T @ w                                                       # (L x n_obs)
-                lm["table"] = self._table(torch.cat([Z, x_obs], 0), spec, center, inv_ls)
-                if spec.weighted:
+                if not spec.gspace:
+                    lm["table"] = self._table(torch.cat([Z, x_obs], 0), spec, center, inv_ls)
+                if spec.weighted or spec.gspace:
                     # predictive mean at the landmarks, m(z) = c + k(z, X_obs) alpha (SOBER/_gp.py:240-253)
                     lm["m_z"] = spec.mean_const + lm["k_oz"].T @ self.ops.f64(spec.alpha)
                     lm["table_obs"] = self._table(x_obs, spec, center, inv_ls)
+                if spec.gspace:
+                    # mu_g(z) = exp(mu_h + var_h / 2) - 1 (SOBER/BASQ/_scale_mmlt.py:208-220); var_h includes the noise
+                    var_z = (spec.outputscale - (lm["k_zo_w"] * lm["k_oz"].T).sum(1) + spec.noise).clamp_min(1e-10)
+                    lm["m_z"] = torch.expm1(lm["m_z"] + 0.5 * var_z)
         return lm
 
     def _basis(self, Z, n_basis, kernel, spec, center, inv_ls, lm):
@@ -212,8 +218,12 @@ class Recombiner:
             gram = self._gram_T(self._points(Z, spec, center, inv_ls), lm["table_z"])        # (L x L)
             if k_zo_w is not None:
                 gram = gram - k_zo_w @ lm["k_oz"]
+            if spec.gspace:
+                gram = torch.expm1(gram)
             if lm["m_z"] is not None:
                 gram = lm["m_z"].unsqueeze(1) * gram * lm["m_z"].unsqueeze(0)
+            if spec.gspace and spec.jitter != 0.0:
+                gram.diagonal().add_(spec.jitter)
             gram = 0.5 * (gram + gram.T)
             if o.gate == "cholesky" and o.defer_gate and o.nystrom_qr != "householder":
                 # the gate's L x L Cholesky only decides: it runs beside the range finder, which speculates on "passed"
@@ -231,7 +241,8 @@ class Recombiner:
             gram = _psd.repair(gram, o.gate)
             U = _nystrom.lowrank_basis(gram, n_basis, qr=o.nystrom_qr, rotate=rotate)
         Um = U if lm["m_z"] is None else U * lm["m_z"].unsqueeze(0)       # weighted mode: the basis carries m(z_l)
-        Uext = Um if k_zo_w is None else torch.cat([Um, -(Um @ k_zo_w)], 1)
+        stacked = k_zo_w is not None and not (spec is not None and spec.gspace)      # linear posterior modes only
+        Uext = torch.cat([Um, -(Um @ k_zo_w)], 1) if stacked else Um
         return U, Uext.contiguous()
 
     def _nystrom(self, Z, n_basis, kernel, spec, center, inv_ls):
@@ -246,6 +257,8 @@ class Recombiner:
     def _accumulate(self, st, alive, n_local, pos0, ES, S, unit=False):
         idx, mu = alive.idx, (None if unit else alive.mass)
         if st["spec"] is not None:
+            if st.get("post") is not None:
+                return self.ops.group_accumulate(st["pts"], st["table"], idx, mu, n_local, pos0, ES, S, post=st["post"])
             return self.ops.group_accumulate(st["pts"], st["table"], idx, mu, n_local, pos0, ES, S, rec=alive.rec,
                                              unit_weights=unit)
         L = st["Z"].shape[0]
@@ -301,7 +314,8 @@ class Recombiner:
         self._bits, self._lut = False, None
         cand_bits = None
         want = None
-        if spec is not None and _lib.RECORD_MAX_D < d <= _lib.BITS_MAX_D and o.k1_variant != 1 and hasattr(ops, "pack_bits"):
+        if (spec is not None and not spec.gspace and _lib.RECORD_MAX_D < d <= _lib.BITS_MAX_D and o.k1_variant != 1
+                and hasattr(ops, "pack_bits")):
             if spec.family == _lib.TANIMOTO:
                 want = "tanimoto"
             elif spec.stationary and spec.inv_ls.numel() == 1:
@@ -338,14 +352,30 @@ class Recombiner:
         obj = None if calc_obj is None else (-1 * calc_obj(pts_rec.to(dev))).to(torch.float64)
         clock.lap("compact+records")
 
-        # weighted mode (SOBER/_kernel.py:33-47): predictive mean of every local candidate, once
+        # weighted mode (SOBER/_kernel.py:33-47): predictive mean m(x) of every local candidate, once;
+        # gspace mode (SOBER/BASQ/_scale_mmlt.py:208-220, 256-275): mu_g(x) = exp(mu_h + var_h / 2) - 1, and the rows
+        # k(x, X_obs) are kept: the POST mode of K1 contracts them with k(z, X_obs) W inside the kernel
         m_x = None
-        if spec is not None and spec.weighted:
+        if spec is not None and (spec.weighted or spec.gspace):
             alpha = ops.f64(spec.alpha)
             m_x = torch.empty(n_rows, dtype=torch.float64, device=dev)
+            n_obs = alpha.numel()
+            kx_all = torch.empty((n_rows, n_obs), dtype=torch.float64, device=dev) if spec.gspace else None
+            wood = ops.f64(spec.woodbury) if spec.gspace else None
             for c0 in range(0, n_rows, 1 << 17):
-                rows = self._gram_T(self._points(X[c0:c0 + (1 << 17)], spec, center, inv_ls), lm["table_obs"])
-                m_x[c0:c0 + (1 << 17)] = spec.mean_const + rows @ alpha
+                c1 = min(n_rows, c0 + (1 << 17))
+                chunk = X[c0:c1]
+                pts_c = self.ops.prepare_points(chunk, center, inv_ls) if (spec.gspace and spec.stationary) \
+                    else self._points(chunk, spec, center, inv_ls)
+                rows = self._gram_T(pts_c, lm["table_obs"])                                  # (m x n_obs)
+                mean = spec.mean_const + rows @ alpha
+                if spec.gspace:
+                    kx_all[c0:c1] = rows
+                    var = (spec.outputscale - ((rows @ wood) * rows).sum(1) + spec.noise).clamp_min(1e-10)
+                    mean = torch.expm1(mean + 0.5 * var)
+                m_x[c0:c1] = mean
+            if spec.gspace:
+                st["post"] = (kx_all, lm["k_zo_w"].contiguous())
         self._m_x = m_x
 
         def k1_pass(alive, n_local, pos0, remaining):

@@ -497,9 +497,12 @@ __global__ void __launch_bounds__(CS_WARPS * 32) car_panel_solve_kernel(const do
 }
 
 // -----------------------------------------------------------------------------------------------------
-// Phi[:, rest] -= U R, zeros in the pivot rows.  128 rows x 64 columns per CTA, 8 x 4 register tile per thread.
+// Phi[:, rest] -= U R, zeros in the pivot rows.  64 rows x 64 columns per CTA, 4 x 4 register tile per thread.
+// (A 128 x 64 tile with 8 x 4 registers took 31-34 us per launch whatever the grid: every CTA ran its load / FMA /
+// read-modify-write phases one after the other with 8 warps -- latency, not throughput.  Four times as many CTAs of a
+// quarter of the work each fill the GPU and the phases of different CTAs overlap on an SM.)
 // -----------------------------------------------------------------------------------------------------
-constexpr int CU_TI = 128, CU_TCOL = 64;
+constexpr int CU_TI = 64, CU_TCOL = 64;
 __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __restrict__ basis,
                                                                   const int* __restrict__ piv,
                                                                   const double* __restrict__ Rt,
@@ -527,20 +530,20 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
         const int j = piv[t0 + t] - i0;
         if (j >= 0 && j < CU_TI) is_piv[j] = 1;
     }
-    // thread (ti, tcx): rows i0 + 32 q + 2 ti + {0, 1} (q < 4: consecutive lanes read consecutive 16-byte chunks of U --
-    // with 8 adjacent rows per thread the LDS.128 were 4-way bank-conflicted and the kernel took 45 us), columns 4 tcx + jj
+    // thread (ti, tcx): rows i0 + 32 q + 2 ti + {0, 1} (q < 2: consecutive lanes read consecutive 16-byte chunks of U),
+    // columns 4 tcx + jj
     const int ti = t & 15, tcx = t >> 4;
-    double acc[4][8];
+    double acc[4][4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.0;
-#pragma unroll 4
+        for (int ii = 0; ii < 4; ++ii) acc[jj][ii] = 0.0;
+#pragma unroll 8
     for (int s = 0; s < CP_NB; ++s) {
-        double a[8], b[4];
+        double a[4], b[4];
         const double2* ap = reinterpret_cast<const double2*>(Us + s * CU_TI + ti * 2);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
             const double2 v = ap[q * 16];
             a[2 * q] = v.x;
             a[2 * q + 1] = v.y;
@@ -550,18 +553,27 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = fma(a[ii], b[jj], acc[jj][ii]);
+            for (int ii = 0; ii < 4; ++ii) acc[jj][ii] = fma(a[ii], b[jj], acc[jj][ii]);
     }
     __syncthreads();                               // is_piv complete
+    double old[4][4];
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+        const int c = c0 + tcx * 4 + jj;
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int il = (ii >> 1) * 32 + ti * 2 + (ii & 1);
+            old[jj][ii] = (c < k && i0 + il < S) ? basis[(size_t)c * S + i0 + il] : 0.0;
+        }
+    }
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
         const int c = c0 + tcx * 4 + jj;
         if (c >= k) continue;
-        double* col = basis + (size_t)c * S + i0;
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
+        for (int ii = 0; ii < 4; ++ii) {
             const int il = (ii >> 1) * 32 + ti * 2 + (ii & 1);
-            if (i0 + il < S) col[il] = is_piv[il] ? 0.0 : col[il] - acc[jj][ii];
+            if (i0 + il < S) basis[(size_t)c * S + i0 + il] = is_piv[il] ? 0.0 : old[jj][ii] - acc[jj][ii];
         }
     }
 }

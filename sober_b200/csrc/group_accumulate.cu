@@ -33,6 +33,11 @@ struct GroupParams {
     const double* Zt;
     const double* zn;
     const double* lut;
+    const double* kx;  // POST: (N x n_obs) candidate-side rows k(x_i, X_obs), addressed by row id like X
+    int64_t ldkx;
+    const double* aw;  // POST: (L x n_obs) landmark-side rows k(z_l, X_obs) W
+    int n_obs;
+    double inner_scale;
     double* out;       // [nsplit][S][L]  (or At itself when nsplit == 1)
     double* totw_out;  // [nsplit][S]
     int64_t row_begin, row_end, rows_per_split;
@@ -242,7 +247,11 @@ constexpr int TN = 64;   // groups per CTA
 constexpr int KC = 16;   // contraction chunk
 constexpr int LDS_ROW = 65;
 
-template <int FAM>
+// POST (SOBER/BASQ/_scale_mmlt.py:256-275): the kernel value enters a NON-LINEAR function of the GP
+// posterior covariance,  v(l, i) = expm1( s k(z_l, x_i) - <aw_l, kx_i> ),  so the stacked-landmark trick of the
+// predictive-covariance mode does not apply: the (L x n_obs).(n_obs x N) contraction runs here, through the same
+// shared-memory tiles as the distance contraction, and never leaves the registers.
+template <int FAM, bool POST = false>
 __global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
     __shared__ double Zs[KC][LDS_ROW];
     __shared__ double Xs[KC][LDS_ROW];
@@ -328,13 +337,47 @@ __global__ void __launch_bounds__(256) group_tiled_kernel(const GroupParams p) {
             }
             __syncthreads();
         }
+        double corr[4][4];
+        if (POST) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) corr[i][j] = 0.0;
+            for (int k0 = 0; k0 < p.n_obs; k0 += KC) {
+                const int k = k0 + kk_ld;
+                const bool kok = k < p.n_obs;
+#pragma unroll
+                for (int pass = 0; pass < 4; ++pass) {
+                    const int c = c_ld + 16 * pass;
+                    const int l = l0 + c;
+                    Zs[kk_ld][c] = (kok && l < p.L) ? __ldg(p.aw + (int64_t)l * p.n_obs + k) : 0.0;
+                    const int64_t row = s_row[c];
+                    Xs[kk_ld][c] = (kok && row >= 0) ? __ldg(p.kx + row * p.ldkx + k) : 0.0;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < KC; ++kk) {
+                    double z[4], x[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) z[i] = Zs[kk][ty + 16 * i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = Xs[kk][tx + 16 * j];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) corr[i][j] = fma(z[i], x[j], corr[i][j]);
+                }
+                __syncthreads();
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const double w = s_w[tx + 16 * j];
             const double xn = s_xn[tx + 16 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const double kv = kernel_value<FAM>(dot[i][j], xn, zn[i], tab_s);
+                double kv = kernel_value<FAM>(dot[i][j], xn, zn[i], tab_s);
+                if (POST) kv = expm1(fma(kv, p.inner_scale, -corr[i][j]));
                 acc[i][j] = fma(kv, w, acc[i][j]);
             }
         }
@@ -557,9 +600,12 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
     pl->row_begin = a->pos0 / a->S;
     pl->row_end = a->n_local > 0 ? ceil_div(hi, a->S) : pl->row_begin;
     const int64_t rows = pl->row_end - pl->row_begin;
-    pl->records = a->rec != nullptr && a->variant != 1;
+    const bool post = a->kx != nullptr || a->aw != nullptr;
+    if (post && (!a->kx || !a->aw || a->n_obs <= 0 || a->ldkx < a->n_obs)) return false;
+    pl->records = a->rec != nullptr && a->variant != 1 && !post;
     pl->bits = a->family == SOBER_TANIMOTO_BITS || a->family == SOBER_HAMMING_LUT;
     if (a->family == SOBER_HAMMING_LUT && !a->lut) return false;
+    if (pl->bits && post) return false;
     if (pl->bits) {
         const int64_t W = a->ldx;
         if (pl->records || a->d <= 0 || W < (a->d + 63) / 64 || !(W == 1 || W == 2 || W == 4 || W == 8 || W == 16 || W == 32))
@@ -633,7 +679,10 @@ static bool launch_bits(const Plan& pl, const GroupParams& p, cudaStream_t st) {
 template <int FAM>
 static bool launch_family(const Plan& pl, const GroupParams& p, cudaStream_t st) {
     if (pl.records) return launch_records_d<FAM>(pl, p, st);
-    group_tiled_kernel<FAM><<<pl.grid, pl.block, 0, st>>>(p);
+    if (p.kx)
+        group_tiled_kernel<FAM, true><<<pl.grid, pl.block, 0, st>>>(p);
+    else
+        group_tiled_kernel<FAM><<<pl.grid, pl.block, 0, st>>>(p);
     return true;
 }
 
@@ -673,12 +722,15 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
     p.S = a->S; p.L = a->L; p.d = a->d;
     p.unit_weights = a->unit_weights;
     p.Zt = a->Zt; p.zn = a->zn; p.lut = a->lut;
+    p.kx = a->kx; p.ldkx = a->ldkx; p.aw = a->aw; p.n_obs = a->n_obs;
+    p.inner_scale = a->outputscale;   // POST: the output scale belongs INSIDE the transform
     p.row_begin = pl.row_begin; p.row_end = pl.row_end; p.rows_per_split = pl.rows_per_split;
     double* ws = (double*)workspace;
+    const double outer_scale = a->kx ? 1.0 : a->outputscale;
     if (pl.nsplit == 1) {
         p.out = a->At;
         p.totw_out = a->totw;
-        p.scale = a->outputscale;
+        p.scale = outer_scale;
     } else {
         p.out = ws;
         p.totw_out = ws + (int64_t)pl.nsplit * SL;
@@ -699,7 +751,7 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
     if (pl.nsplit > 1) {
         const int64_t n = SL > a->S ? SL : a->S;
         reduce_splits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, ws + (int64_t)pl.nsplit * SL, pl.nsplit,
-                                                                        SL, a->S, a->outputscale, a->At, a->totw);
+                                                                        SL, a->S, outer_scale, a->At, a->totw);
         SOBER_LAUNCH_CHECK("reduce_splits");
     }
     return SOBER_OK;

@@ -9,7 +9,7 @@ from oracle import rchq as oracle_rchq
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["matern6d_rest", "matern6d_pow2", "rbf2d_branin", "rbf_ard5d", "ising24_hamming", "tanimoto256",
-         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d", "wpredcov_matern6d"]
+         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d", "wpredcov_matern6d", "gspace_matern4d"]
 LOOP_CASES = [c for c in CASES if c not in ("direct_branch", "tiny_passthrough")]
 
 
@@ -45,6 +45,10 @@ class Case:
 
     def kernel(self):
         cov = ok.make_kernel(self.fam, self.ls if self.ls is not None else 1.0, self.os).to(self.device)
+        if self.mode == "gspace":       # BASQ's kernel: bound method of the (restated) ScaleMmltGP, SOBER/BASQ/_basq.py:55-67
+            from oracle import gspace as ogs
+            const = float(self.raw["const"]) if "const" in self.raw else 0.0
+            return ogs.ScaleMmltGP(ok.GPModel(cov, self.Xobs, self.yobs, noise=self.noise, mean_constant=const)).gspace_kernel
         if self.mode == "kernel":
             return ok.Kernel(ok.BareModel(cov), mode="kernel")
         return ok.Kernel(ok.GPModel(cov, self.Xobs, self.yobs, noise=self.noise), mode=self.mode)

@@ -71,7 +71,8 @@ class TorchOps:
         idx = torch.nonzero(mu != 0).reshape(-1).to(torch.int32)
         return idx, mu[idx.long()].clone(), int(idx.numel())
 
-    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None, rec=None, unit_weights=False):
+    def group_accumulate(self, pts, lm, idx, mu, n_local, pos0, ES, S, n_global=None, rec=None, unit_weights=False,
+                         post=None):
         L, d = lm.L, lm.d
         at = torch.zeros((S, L), dtype=torch.float64)
         totw = torch.zeros(S, dtype=torch.float64)
@@ -88,6 +89,16 @@ class TorchOps:
         if lm.family == HAMMING_LUT:
             ham = (xn + lm.zn.reshape(1, -1) - 2.0 * (x @ lm.zt.T)).round().long()
             kv = lm.lut[ham] * w.reshape(-1, 1)
+        elif post is not None:
+            # non-linear posterior mode (csrc/group_accumulate.cu, POST): expm1(s k(z, x) - <aw_l, kx_i>)
+            kx, aw = post
+            base = kernel_values(x @ lm.zt.T, xn, lm.zn.reshape(1, -1), lm.family) * lm.outputscale
+            kv = torch.expm1(base - kx[rows] @ aw.T) * w.reshape(-1, 1)
+            pos = pos0 + torch.arange(n_local)
+            at.index_add_(0, pos % S, kv)
+            inside = pos < ES
+            totw.index_add_(0, (pos % S)[inside], w[inside])
+            return at, totw
         else:
             kv = kernel_values(x @ lm.zt.T, xn, lm.zn.reshape(1, -1), lm.family) * w.reshape(-1, 1)
         pos = pos0 + torch.arange(n_local)

@@ -171,6 +171,14 @@ def case_inputs(name):
         yo = 1.5 + torch.sin(3.0 * Xo).sum(-1) + 0.05 * torch.randn(30, dtype=f64, generator=g)
         return dict(X=X, Z=Z, mu=_weights(3072, 0, g), b=24, fam="matern", ls=[0.6], os=1.0,
                     mode="weighted_predictive_covariance", Xobs=Xo, yobs=yo, noise=1e-2)
+    if name == "gspace_matern4d":        # BASQ.quadrature (SOBER/BASQ/_basq.py:55-67): kernel = ScaleMmltGP.gspace_kernel,
+        X = torch.rand(2400, 4, dtype=f64, generator=g)     # uniform weights, X_nys = the first candidates
+        Z = X[:64].clone()
+        Xo = torch.rand(24, 4, dtype=f64, generator=g)
+        yo = torch.log1p(torch.exp(-4.0 * ((Xo - 0.5) ** 2).sum(-1)))          # h-space targets log(g + 1)
+        mu = torch.ones(2400, dtype=f64) / 2400
+        return dict(X=X, Z=Z, mu=mu, b=16, fam="matern", ls=[0.7], os=0.9, mode="gspace", Xobs=Xo, yobs=yo,
+                    noise=1e-3, const=0.05)
     if name == "direct_branch":          # n+1 < N <= 2(n+1): a single CAR on the points themselves
         X = torch.rand(40, 3, dtype=f64, generator=g)
         Z = X[:30].clone()
@@ -188,13 +196,21 @@ def case_inputs(name):
 
 
 CASES = ["matern6d_rest", "matern6d_pow2", "rbf2d_branin", "rbf_ard5d", "ising24_hamming", "tanimoto256",
-         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d", "wpredcov_matern6d"]
+         "predcov_matern6d", "direct_branch", "tiny_passthrough", "objective_matern4d", "wpredcov_matern6d", "gspace_matern4d"]
 
 
 def build_kernel(spec):
     cov = ok.make_kernel(spec["fam"], spec["ls"] if spec["ls"] is not None else 1.0, spec["os"])
     if spec["mode"] == "kernel":
         return ok.Kernel(ok.BareModel(cov), mode="kernel")
+    if spec["mode"] == "gspace":
+        # the REFERENCE's own bound method (unmodified SOBER/BASQ/_scale_mmlt.py on a stand-in model)
+        import importlib.util as _ilu
+        _s = _ilu.spec_from_file_location("mggs", os.path.join(HERE, "make_golden_gspace.py"))
+        _m = _ilu.module_from_spec(_s)
+        _s.loader.exec_module(_m)
+        model = ok.GPModel(cov, spec["Xobs"], spec["yobs"], noise=spec["noise"], mean_constant=spec["const"])
+        return _m.reference_instance(model).gspace_kernel
     model = ok.GPModel(cov, spec["Xobs"], spec.get("yobs"), noise=spec["noise"])
     return ok.Kernel(model, mode=spec["mode"])
 
@@ -245,6 +261,8 @@ def main():
             out["noise"] = np.float64(spec["noise"])
         if "yobs" in spec:
             out["yobs"] = spec["yobs"].numpy()
+        if "const" in spec:
+            out["const"] = np.float64(spec["const"])
         n_car = 0
         for stage, payload in stages:
             if stage == "basis":

@@ -112,6 +112,29 @@ def test_gram_other_matern_orders(ops, cuda_device, nu):
     assert float(((got - want).abs() * mask).max()) < 1e-11
 
 
+def test_gspace_post_kernel_gram_matches_oracle(ops, cuda_device):
+    """POST mode of K1 (non-linear in the posterior covariance, SOBER/BASQ/_scale_mmlt.py:256-275): the Gram
+    expm1(cov_h(z, x)) against the oracle's gspace_kernel divided by its mu_g factors, 1e-10 relative."""
+    from sober_b200 import Recombiner
+    from sober_b200._kernel_spec import introspect
+    case = Case("gspace_matern4d", cuda_device)
+    kern = case.kernel()
+    spec = introspect(kern)
+    assert spec is not None and spec.gspace
+    rec = Recombiner(ops)
+    center, inv_ls = scaled(spec, case.Z, cuda_device)
+    lm = rec._landmarks(case.Z, spec, center, inv_ls)
+    X = case.X[:777]
+    pts = ops.prepare_points(X, center, inv_ls)
+    kx = rec._gram_T(pts, lm["table_obs"])
+    at, _ = ops.group_accumulate(pts, lm["table_z"], None, None, len(X), 0, 0, len(X), post=(kx, lm["k_zo_w"].contiguous()))
+    owner = kern.__self__
+    want = owner.gspace_kernel(case.Z, X) / (owner.gspace_mean_predict(case.Z).unsqueeze(1) *
+                                              owner.gspace_mean_predict(X).unsqueeze(0))
+    assert rel(at.T, want) < 1e-10
+    assert rel(lm["m_z"], owner.gspace_mean_predict(case.Z)) < 1e-10
+
+
 # ------------------------------------------------------------------------------------------------------------
 # P1: group sums per iteration (remainder quirk included), against the oracle's trace
 # ------------------------------------------------------------------------------------------------------------
@@ -123,7 +146,7 @@ def test_group_accumulate_matches_oracle_trace(ops, cuda_device, name, variant):
     case = Case(name)                                   # oracle on the CPU
     if case.objective is not None:
         pytest.skip("objective branch covered end-to-end")
-    if case.mode == "weighted_predictive_covariance":
+    if case.mode in ("weighted_predictive_covariance", "gspace"):
         pytest.skip("the K1 weights carry m(x) inside Recombiner.run: covered end-to-end")
     groups, updates = [], []
 
@@ -544,7 +567,7 @@ def test_end_to_end_against_reference_fixture(ops, cuda_device, name):
 
 
 @pytest.mark.parametrize("name", ["matern6d_rest", "matern6d_pow2", "rbf_ard5d", "ising24_hamming", "tanimoto256",
-                                  "predcov_matern6d"])
+                                  "predcov_matern6d", "wpredcov_matern6d", "gspace_matern4d"])
 def test_parity_mode_equals_oracle_on_same_device(ops, cuda_device, name):
     """parity mode vs the oracle executing the reference's op sequence on the SAME device (same CUDA generator
     draw for svd_lowrank, same cuSOLVER SVD for the null space): identical points, weights to 1e-6."""
@@ -567,7 +590,8 @@ def test_parity_mode_equals_oracle_on_same_device(ops, cuda_device, name):
         assert float((mu_g - mu_o).abs().max()) < 1e-6
 
 
-@pytest.mark.parametrize("name", ["matern6d_rest", "matern6d_pow2", "rbf_ard5d", "tanimoto256", "predcov_matern6d"])
+@pytest.mark.parametrize("name", ["matern6d_rest", "matern6d_pow2", "rbf_ard5d", "tanimoto256", "predcov_matern6d",
+                                  "ising24_hamming", "wpredcov_matern6d", "gspace_matern4d", "objective_matern4d"])
 def test_fast_mode_equals_cpu_oracle_with_projector_nullspace(ops, cuda_device, name):
     """fast mode (CUDA Gram, Cholesky gate, projector null space, cluster elimination kernel) vs the CPU oracle fed
     the same test matrix and the same null-space construction restated with LAPACK (tests/_cases.py)."""
@@ -583,7 +607,7 @@ def test_fast_mode_equals_cpu_oracle_with_projector_nullspace(ops, cuda_device, 
             warnings.simplefilter("ignore")
             mu_o = None if cpu.mu is None else cpu.mu.clone()
             idx_o, w_o = oracle.recombination(cpu.X, cpu.Z, cpu.b, cpu.kernel(), None, None, init_weights=mu_o,
-                                              nullspace=projector_nullspace)
+                                              nullspace=projector_nullspace, calc_obj=cpu.objective)
     finally:
         torch.randn = orig
     gpu = Case(name, cuda_device)
@@ -592,7 +616,8 @@ def test_fast_mode_equals_cpu_oracle_with_projector_nullspace(ops, cuda_device, 
         with warnings.catch_warnings(), sober_b200.configure(mode="fast"):
             warnings.simplefilter("ignore")
             mu_g = None if gpu.mu is None else gpu.mu.clone()
-            idx_g, w_g = sober_b200.recombination(gpu.X, gpu.Z, gpu.b, gpu.kernel(), None, None, init_weights=mu_g)
+            idx_g, w_g = sober_b200.recombination(gpu.X, gpu.Z, gpu.b, gpu.kernel(), None, None, init_weights=mu_g,
+                                                  calc_obj=gpu.objective)
     finally:
         _nystrom._injected_test_matrix = None
     assert torch.equal(idx_g.cpu(), idx_o)

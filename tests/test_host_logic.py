@@ -53,7 +53,7 @@ def test_invariants_every_mode(name):
 
 
 @pytest.mark.parametrize("name", ["matern6d_rest", "rbf_ard5d", "ising24_hamming", "tanimoto256",
-                                  "predcov_matern6d"])
+                                  "predcov_matern6d", "wpredcov_matern6d", "gspace_matern4d"])
 def test_generic_callable_path_matches_fused(name):
     case = Case(name)
     idx_f, w_f, _ = run_host(case, "parity")
