@@ -618,17 +618,18 @@ class Recombiner:
 # ---------------------------------------------------------------------------------------------------------
 # public entry point
 # ---------------------------------------------------------------------------------------------------------
-_default_ops = None
+_default_ops = {}      # one CudaOps (workspaces, graph caches, partition stream) per CUDA device index
 _default_comm = None
 
 
 def _ops():
-    global _default_ops
-    if _default_ops is None:
-        from ._ops import CudaOps
-        _default_ops = CudaOps()
-    _default_ops.variant = options.k1_variant
-    return _default_ops
+    from ._ops import CudaOps
+    key = torch.cuda.current_device() if torch.cuda.is_available() else -1
+    ops = _default_ops.get(key)
+    if ops is None:
+        ops = _default_ops[key] = CudaOps()
+    ops.variant = options.k1_variant
+    return ops
 
 
 def set_communicator(comm):

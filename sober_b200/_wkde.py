@@ -22,7 +22,14 @@ from . import _lib
 from ._ops import LandmarkTable
 
 _GROUPS = 4            # = REC_TG of csrc/group_accumulate.cu: a full register tile
-_MAX_QUERIES = 1 << 24  # per launch (grid.y limit of K1: 65535 * 512 landmarks)
+# queries per launch: grid.y of K1 is limited to 65535 blocks of 512 "landmarks" (record kernel, d <= 8) or of 64 (tiled
+# kernel of the indexed layout, d > 8)
+_MAX_QUERIES_RECORDS = 1 << 24
+_MAX_QUERIES_TILED = 65535 * 64 // 2
+
+
+def _max_queries(d):
+    return _MAX_QUERIES_RECORDS if d <= _lib.RECORD_MAX_D else _MAX_QUERIES_TILED
 
 
 def wkde_pdf(centres, weights, covariance, queries, bounds=None, constant=None, ops=None):
@@ -61,11 +68,12 @@ def wkde_pdf(centres, weights, covariance, queries, bounds=None, constant=None, 
         pts, rec, mu = None, ops.make_records(cw, center, inv_ls, None, w).rec, None
     else:
         pts, rec, mu = ops.prepare_points(cw, center, inv_ls), None, w
-    for s in range(0, q.shape[0], _MAX_QUERIES):
-        v = ((q[s:s + _MAX_QUERIES] @ inv_t) - center) * inv_ls
+    step = _max_queries(d)
+    for s in range(0, q.shape[0], step):
+        v = ((q[s:s + step] @ inv_t) - center) * inv_ls
         table = LandmarkTable((-2.0 * v).contiguous(), (v * v).sum(-1).contiguous(), _lib.RBF, 1.0)
         at, _ = ops.group_accumulate(pts, table, None, mu, n_pad, 0, n_pad, _GROUPS, rec=rec)
-        out[s:s + _MAX_QUERIES] = at.sum(0) * scale
+        out[s:s + step] = at.sum(0) * scale
     if bounds is not None:
         b = ops.f64(bounds)
         out[(q < b[0]).any(1) | (q > b[1]).any(1)] = 0.0
