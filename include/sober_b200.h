@@ -112,7 +112,9 @@ int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_out, double*
  *   LUT family), lut as described at the enum.
  * At: S x L (transposed on purpose: coalesced stores and it is the left operand of the projection).
  * workspace holds the per-split partial sums (deterministic two-stage reduction, no atomics).
- * variant: 0 = automatic (records -> register kernel, else tiled), 1 = force the generic tiled kernel.
+ * variant: 0 = automatic (records -> register kernel, else tiled; SOBER_TANIMOTO_BITS with 256..1024-bit rows and at least
+ *          2^20 pairs -> the tcgen05 kernel of csrc/group_bits_mma.cu), 1 = force the generic tiled kernel,
+ *          4 = force the popcount kernel for SOBER_TANIMOTO_BITS.
  * ------------------------------------------------------------------------------------------------- */
 typedef struct sober_group_args {
     const double* X;

@@ -19,6 +19,25 @@
 
 namespace sober {
 
+// csrc/group_bits_mma.cu: Tanimoto on bit-packed rows through tcgen05 (kind::i8)
+struct BitsMmaParams {
+    const uint64_t* X;
+    const uint64_t* Z;
+    const double* xn;
+    int64_t xn_stride;
+    const double* zn;
+    const int32_t* idx;
+    const double* mu;
+    int64_t n_local, pos0, ES;
+    int S, L, W;
+    double* out;
+    double* totw_out;
+    int64_t row_begin, row_end, rows_per_split;
+    double scale;
+};
+bool bits_mma_supported(int W);
+int launch_bits_mma(const BitsMmaParams& p, dim3 grid, cudaStream_t st);
+
 struct GroupParams {
     const double* X;
     int64_t ldx;
@@ -587,6 +606,7 @@ constexpr int BITS_TG = 4;
 static int bits_tl(int W) { return W <= 8 ? 4 : (W <= 16 ? 2 : 1); }
 
 struct Plan {
+    bool bits_mma;     // bit-packed Tanimoto on the tensor cores (csrc/group_bits_mma.cu)
     bool records;
     bool bits;
     dim3 grid, block;
@@ -613,7 +633,14 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
     }
     if (pl->records && (a->d > 8 || a->ldr != (a->d + 3) / 2 * 2)) return false;
     int64_t gx, gy, target;
-    if (pl->bits) {
+    pl->bits_mma = a->family == SOBER_TANIMOTO_BITS && a->variant != 4 && bits_mma_supported((int)a->ldx) &&
+                   a->n_local * (int64_t)a->L >= (1 << 20);
+    if (pl->bits_mma) {
+        gx = ceil_div(a->S, 128);
+        gy = ceil_div(a->L, 64);
+        pl->block = dim3(288);
+        target = (int64_t)sm_count() * 3;    // one 167 KB CTA per SM, a few waves
+    } else if (pl->bits) {
         gx = ceil_div(a->S, BITS_TG);
         gy = ceil_div(a->L, 8 * 32 * bits_tl((int)a->ldx));
         pl->block = dim3(256);
@@ -735,6 +762,23 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
         p.out = ws;
         p.totw_out = ws + (int64_t)pl.nsplit * SL;
         p.scale = 1.0;
+    }
+    if (pl.bits_mma) {
+        BitsMmaParams q;
+        q.X = reinterpret_cast<const uint64_t*>(a->X); q.Z = reinterpret_cast<const uint64_t*>(a->Zt);
+        q.xn = a->xn; q.xn_stride = a->xn_stride; q.zn = a->zn; q.idx = a->idx; q.mu = a->mu;
+        q.n_local = a->n_local; q.pos0 = a->pos0; q.ES = a->ES; q.S = a->S; q.L = a->L; q.W = (int)a->ldx;
+        q.out = p.out; q.totw_out = p.totw_out;
+        q.row_begin = pl.row_begin; q.row_end = pl.row_end; q.rows_per_split = pl.rows_per_split; q.scale = p.scale;
+        const int rc = launch_bits_mma(q, pl.grid, st);
+        if (rc != SOBER_OK) return rc;
+        if (pl.nsplit > 1) {
+            const int64_t n = SL > a->S ? SL : a->S;
+            reduce_splits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(ws, ws + (int64_t)pl.nsplit * SL, pl.nsplit,
+                                                                            SL, a->S, outer_scale, a->At, a->totw);
+            SOBER_LAUNCH_CHECK("reduce_splits");
+        }
+        return SOBER_OK;
     }
     bool ok = false;
     switch (a->family) {

@@ -1,0 +1,278 @@
+// K1 for Tanimoto on bit-packed fingerprints, on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// <x, z> over {0,1}^d is an integer GEMM: 0/1 operands are exact in 8 bits and the counts (<= 2048) in the int32
+// accumulators, so `tcgen05.mma.kind::i8` computes popcount(x & z) EXACTLY -- the same integers as the popcount kernel
+// (group_bits_kernel), whose 16 POPC per clock per SM bound C4 at 84 ms per step.  Replaces SOBER/_rchq.py:124-136 for
+// SOBER/_drug_modelling.py:15-25 exactly like the other K1 kernels (same contract: At, totw, the remainder quirk).
+//
+// CTA = 128 groups (one candidate per group and row) x 64 landmarks.  Warp roles:
+//   warps 0-3  EXPANDERS  thread r owns candidate row r of the current row: gathers its bit-packed words from HBM
+//                         (128 B per 1024-bit fingerprint: HBM traffic stays that of the packed format) and expands them
+//                         to 0/1 bytes straight into the shared-memory operand tile of the MMA (canonical K-major,
+//                         no-swizzle layout: 16-byte K-chunks, rows 16 bytes apart), 256 K-elements per pipeline stage;
+//   warp  8    MMA        one thread issues 8 x tcgen05.mma (M=128, N=64, K=32) per stage into one of two accumulator
+//                         stages in TMEM (64 int32 columns each), tcgen05.commit releases the stage / publishes the tile;
+//   warps 4-7  EPILOGUE   tcgen05.ld of the lane's 64 dot products, FP64 Tanimoto ratio (the arithmetic of
+//                         tanimoto_value(), common.cuh), weighted accumulation into 64 FP64 registers per thread.
+// The landmark tile (64 x d bytes) is expanded once per CTA and stays resident in shared memory.
+#include "common.cuh"
+
+namespace sober {
+
+constexpr int BM_TM = 128;        // candidates (groups) per tile = TMEM lanes
+constexpr int BM_TN = 64;         // landmarks per CTA = accumulator columns
+constexpr int BM_KB = 256;        // K elements (bits -> bytes) per pipeline stage
+constexpr int BM_STAGES = 3;
+constexpr int BM_THREADS = 288;   // 4 expander warps + 4 epilogue warps + 1 MMA warp
+constexpr int BM_MAXW = 16;       // words per row (1024 bits); wider rows use the popcount kernel
+
+struct BitsMmaParams {
+    const uint64_t* X;            // candidate words, row stride W
+    const uint64_t* Z;            // landmark words, row stride W
+    const double* xn;             // candidate popcounts
+    int64_t xn_stride;
+    const double* zn;             // landmark popcounts
+    const int32_t* idx;
+    const double* mu;
+    int64_t n_local, pos0, ES;
+    int S, L, W;
+    double* out;                  // [nsplit][S][L]
+    double* totw_out;             // [nsplit][S]
+    int64_t row_begin, row_end, rows_per_split;
+    double scale;
+};
+
+__device__ __forceinline__ void bm_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bm_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bm_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar))
+                 : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 bytes (rows 16 B apart);
+// LBO = byte distance of the two 16-byte K-chunks of one MMA, SBO = byte distance of consecutive 8-row groups
+__device__ __forceinline__ uint64_t bm_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void bm_mma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void bm_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __maxnreg__(224) group_bits_mma_kernel(const BitsMmaParams p) {
+    extern __shared__ __align__(128) unsigned char bm_smem[];
+    const int K = p.W * 64;                          // K elements = bits
+    const int nkb = K / BM_KB;                       // pipeline stages per tile
+    unsigned char* Bs = bm_smem;                     // [K/16][64][16]
+    unsigned char* As = Bs + (size_t)BM_TN * K;      // [stages][16][128][16]
+    uint64_t* lut8 = reinterpret_cast<uint64_t*>(As + (size_t)BM_STAGES * BM_TM * BM_KB);   // [256]
+    double* meta = reinterpret_cast<double*>(lut8 + 256);                                   // [4][128][2]  (w, |x|^2)
+    double* zn_s = meta + 4 * BM_TM * 2;                                                    // [64]
+    __shared__ __align__(8) uint64_t full_bar[BM_STAGES], empty_bar[BM_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int g0 = blockIdx.x * BM_TM;
+    const int l0 = blockIdx.y * BM_TN;
+    const int64_t r0 = p.row_begin + (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t r1 = min(p.row_end, r0 + p.rows_per_split);
+    const int64_t hi = p.pos0 + p.n_local;
+    const int ntiles = (int)max((int64_t)0, r1 - r0);
+
+    if (t == 0) {
+        for (int s = 0; s < BM_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        mbar_fence_init();
+    }
+    // byte -> 8 bytes of 0/1
+    for (int b = t; b < 256; b += BM_THREADS) {
+        uint64_t v = 0;
+        for (int i = 0; i < 8; ++i) v |= (uint64_t)((b >> i) & 1) << (8 * i);
+        lut8[b] = v;
+    }
+    if (t < BM_TN) zn_s[t] = (l0 + t < p.L) ? p.zn[l0 + t] : 0.0;
+    if (warp == 8) {                                 // TMEM: 2 accumulator stages x 64 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_addr(&tmem_base_s))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    __syncthreads();                                 // lut8 ready
+    // resident landmark operand: chunk kc (16 K-elements) of landmark n at Bs[(kc * 64 + n) * 16]
+    for (int c = t; c < BM_TN * (K / 16); c += BM_THREADS) {
+        const int n = c % BM_TN, kc = c / BM_TN;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (l0 + n < p.L) {
+            const uint64_t word = __ldg(p.Z + (int64_t)(l0 + n) * p.W + (kc >> 2));
+            const uint32_t bits = (uint32_t)(word >> (16 * (kc & 3))) & 0xffffu;
+            const uint64_t lo = lut8[bits & 0xff], hh = lut8[bits >> 8];
+            val = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hh, (uint32_t)(hh >> 32));
+        }
+        *reinterpret_cast<uint4*>(Bs + ((size_t)kc * BM_TN + n) * 16) = val;
+    }
+    bm_fence_async();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ================= EXPANDERS =================
+        const int r = t;                              // row of the tile
+        const int g = g0 + r;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int64_t e = r0 + it;
+            const int64_t pos = e * p.S + g;
+            const bool ok = g < p.S && pos >= p.pos0 && pos < hi;
+            int64_t row = 0;
+            double w = 0.0, xn = 0.0;
+            if (ok) {
+                const int64_t loc = pos - p.pos0;
+                row = p.idx ? (int64_t)__ldg(p.idx + loc) : loc;
+                w = p.mu ? __ldg(p.mu + loc) : 1.0;
+                xn = __ldg(p.xn + row * p.xn_stride);
+            }
+            double* m = meta + ((size_t)(it & 3) * BM_TM + r) * 2;
+            m[0] = w;
+            m[1] = xn;
+            const uint64_t* src = p.X + row * p.W;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                unsigned char* dst = As + (size_t)stage * BM_TM * BM_KB;
+#pragma unroll
+                for (int wd = 0; wd < BM_KB / 64; ++wd) {
+                    const uint64_t word = ok ? __ldg(src + kb * (BM_KB / 64) + wd) : 0ull;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const uint32_t bits = (uint32_t)(word >> (16 * c)) & 0xffffu;
+                        const uint64_t lo = lut8[bits & 0xff], hh = lut8[bits >> 8];
+                        *reinterpret_cast<uint4*>(dst + ((size_t)(wd * 4 + c) * BM_TM + r) * 16) =
+                            make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hh, (uint32_t)(hh >> 32));
+                    }
+                }
+                bm_fence_async();                     // generic-proxy writes -> visible to the tensor core (async proxy)
+                bm_arrive(&full_bar[stage]);
+                if (++stage == BM_STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 8) {
+        // ================= MMA ISSUER =================
+        if (lane == 0) {
+            // instruction descriptor: D = s32, A = B = unsigned 8-bit, both K-major, N = 64, M = 128
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(BM_TN >> 3) << 17) | ((uint32_t)(BM_TM >> 4) << 24);
+            const uint32_t a_base = smem_addr(As), b_base = smem_addr(Bs);
+            int stage = 0;
+            uint32_t phase = 0, tphase[2] = {0, 0};
+            for (int it = 0; it < ntiles; ++it) {
+                const int acc = it & 1;
+                mbar_wait(&tempty_bar[acc], tphase[acc] ^ 1u);     // epilogue has drained this accumulator stage
+                tphase[acc] ^= 1u;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * BM_TN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < BM_KB / 32; ++j) {
+                        const uint64_t adesc = bm_desc(a_base + (uint32_t)stage * BM_TM * BM_KB + (uint32_t)j * 2u * BM_TM * 16u,
+                                                       BM_TM * 16u, 128u);
+                        const uint64_t bdesc = bm_desc(b_base + (uint32_t)(kb * (BM_KB / 16) + 2 * j) * BM_TN * 16u,
+                                                       BM_TN * 16u, 128u);
+                        bm_mma_i8(d_tmem, adesc, bdesc, idesc, (kb | j) != 0 ? 1u : 0u);
+                    }
+                    bm_commit(&empty_bar[stage]);     // the stage is free once these MMAs have read it
+                    if (++stage == BM_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                bm_commit(&tfull_bar[acc]);           // accumulator of this tile complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= EPILOGUE =================
+        const int q = warp - 4;                       // TMEM lane quarter: this warp may access lanes [32 q, 32 q + 32)
+        const int r = 32 * q + lane;                  // row of the tile = TMEM lane
+        const int g = g0 + r;
+        double acc[BM_TN];
+#pragma unroll
+        for (int l = 0; l < BM_TN; ++l) acc[l] = 0.0;
+        double tw = 0.0;
+        uint32_t tphase[2] = {0, 0};
+        for (int it = 0; it < ntiles; ++it) {
+            const int a = it & 1;
+            mbar_wait(&tfull_bar[a], tphase[a]);
+            tphase[a] ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const double* m = meta + ((size_t)(it & 3) * BM_TM + r) * 2;
+            const double w = m[0], xn = m[1];
+            const int64_t pos = (r0 + it) * p.S + g;
+            if (w != 0.0 && blockIdx.y == 0 && pos < p.ES) tw += w;
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)a * BM_TN;
+            // two halves of 32 columns: 64 dot products + 64 FP64 accumulators would not fit the register file
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t v[32];
+                bm_tmem_ld32(taddr + 32u * h, v);
+                if (h == 1) {
+                    // the accumulator stage is in registers: hand it back to the MMA warp before the FP64 work
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) bm_arrive(&tempty_bar[a]);
+                }
+                if (w != 0.0) {
+#pragma unroll
+                    for (int l = 0; l < 32; ++l)
+                        acc[32 * h + l] = fma(tanimoto_value((double)(int)v[l], xn, zn_s[32 * h + l]), w, acc[32 * h + l]);
+                }
+            }
+        }
+        if (g < p.S) {
+            double* out = p.out + ((int64_t)blockIdx.z * p.S + g) * p.L + l0;
+#pragma unroll
+            for (int l = 0; l < BM_TN; ++l)
+                if (l0 + l < p.L) out[l] = acc[l] * p.scale;
+            if (blockIdx.y == 0) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 8) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+size_t bits_mma_smem(int W) {
+    const size_t K = (size_t)W * 64;
+    return (size_t)BM_TN * K + (size_t)BM_STAGES * BM_TM * BM_KB + 256 * 8 + 4 * BM_TM * 2 * 8 + BM_TN * 8 + 128;
+}
+
+bool bits_mma_supported(int W) { return W >= 4 && W <= BM_MAXW && W % 4 == 0; }
+
+int launch_bits_mma(const BitsMmaParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = bits_mma_smem(p.W);
+    static int configured[64] = {};
+    int dev = 0;
+    SOBER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || configured[dev] < (int)smem) {
+        SOBER_CUDA_CHECK(cudaFuncSetAttribute(group_bits_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[dev] = (int)smem;
+    }
+    group_bits_mma_kernel<<<grid, BM_THREADS, smem, st>>>(p);
+    SOBER_LAUNCH_CHECK("group_bits_mma");
+    return SOBER_OK;
+}
+
+}  // namespace sober

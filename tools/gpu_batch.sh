@@ -23,6 +23,9 @@ for step in "$@"; do
     mbench4)  TMO=900 TAILN=3 run bench_4gpu python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 5 --warmup 3 ;;
     mbench8)  TMO=900 TAILN=3 run bench_8gpu python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 5 --warmup 3 ;;
     projbrk)  TAILN=30 run projector_breakdown python tools/projector_breakdown.py ;;
+    bitsmma)  TMO=240 TAILN=25 run bits_mma_tests python -m pytest tests/test_bits_mma.py -x -q -m gpu ;;
+    bench4)   TMO=600 TAILN=3 run bench_c4 python bench.py --workload c4 --steps 3 --warmup 2 --no-cpu-baseline ;;
+    bench3)   TMO=600 TAILN=3 run bench_c3 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline ;;
     stagepar) TAILN=25 run stage_c2_parity python tools/stage_breakdown.py c2 parity ;;
     bench2)   TMO=600 TAILN=3 run bench_c2 python bench.py --steps 10 --warmup 3 ;;
     bench5)   TMO=600 TAILN=3 run bench_c5 python bench.py --workload c5 --steps 5 --warmup 2 --no-cpu-baseline ;;
