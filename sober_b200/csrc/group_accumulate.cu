@@ -638,7 +638,7 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
     if (pl->bits_mma) {
         gx = ceil_div(a->S, 128);
         gy = ceil_div(a->L, 64);
-        pl->block = dim3(288);
+        pl->block = dim3(416);
         target = (int64_t)sm_count() * 3;    // one 167 KB CTA per SM, a few waves
     } else if (pl->bits) {
         gx = ceil_div(a->S, BITS_TG);

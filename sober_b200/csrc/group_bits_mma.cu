@@ -10,10 +10,10 @@
 //                         (128 B per 1024-bit fingerprint: HBM traffic stays that of the packed format) and expands them
 //                         to 0/1 bytes straight into the shared-memory operand tile of the MMA (canonical K-major,
 //                         no-swizzle layout: 16-byte K-chunks, rows 16 bytes apart), 256 K-elements per pipeline stage;
-//   warp  8    MMA        one thread issues 8 x tcgen05.mma (M=128, N=64, K=32) per stage into one of two accumulator
+//   warp  12   MMA        one thread issues 8 x tcgen05.mma (M=128, N=64, K=32) per stage into one of two accumulator
 //                         stages in TMEM (64 int32 columns each), tcgen05.commit releases the stage / publishes the tile;
-//   warps 4-7  EPILOGUE   tcgen05.ld of the lane's 64 dot products, FP64 Tanimoto ratio (the arithmetic of
-//                         tanimoto_value(), common.cuh), weighted accumulation into 64 FP64 registers per thread.
+//   warps 4-11 EPILOGUE   (two warps per TMEM lane quarter, 32 columns each) tcgen05.ld of the lane's dot products, FP64 Tanimoto ratio (the arithmetic of
+//                         tanimoto_value(), common.cuh), weighted accumulation into 32 FP64 registers per thread.
 // The landmark tile (64 x d bytes) is expanded once per CTA and stays resident in shared memory.
 #include "common.cuh"
 
@@ -23,7 +23,8 @@ constexpr int BM_TM = 128;        // candidates (groups) per tile = TMEM lanes
 constexpr int BM_TN = 64;         // landmarks per CTA = accumulator columns
 constexpr int BM_KB = 256;        // K elements (bits -> bytes) per pipeline stage
 constexpr int BM_STAGES = 3;
-constexpr int BM_THREADS = 288;   // 4 expander warps + 4 epilogue warps + 1 MMA warp
+constexpr int BM_THREADS = 416;   // 4 expander warps + 8 epilogue warps (two per TMEM lane quarter) + 1 MMA warp
+constexpr int BM_MMA_WARP = 12;
 constexpr int BM_MAXW = 16;       // words per row (1024 bits); wider rows use the popcount kernel
 
 struct BitsMmaParams {
@@ -71,7 +72,7 @@ __device__ __forceinline__ void bm_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __maxnreg__(224) group_bits_mma_kernel(const BitsMmaParams p) {
+__global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const BitsMmaParams p) {
     extern __shared__ __align__(128) unsigned char bm_smem[];
     const int K = p.W * 64;                          // K elements = bits
     const int nkb = K / BM_KB;                       // pipeline stages per tile
@@ -93,7 +94,7 @@ __global__ void __maxnreg__(224) group_bits_mma_kernel(const BitsMmaParams p) {
 
     if (t == 0) {
         for (int s = 0; s < BM_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
         mbar_fence_init();
     }
     // byte -> 8 bytes of 0/1
@@ -103,7 +104,7 @@ __global__ void __maxnreg__(224) group_bits_mma_kernel(const BitsMmaParams p) {
         lut8[b] = v;
     }
     if (t < BM_TN) zn_s[t] = (l0 + t < p.L) ? p.zn[l0 + t] : 0.0;
-    if (warp == 8) {                                 // TMEM: 2 accumulator stages x 64 columns
+    if (warp == BM_MMA_WARP) {                       // TMEM: 2 accumulator stages x 64 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_addr(&tmem_base_s))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -168,7 +169,7 @@ __global__ void __maxnreg__(224) group_bits_mma_kernel(const BitsMmaParams p) {
                 if (++stage == BM_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == BM_MMA_WARP) {
         // ================= MMA ISSUER =================
         if (lane == 0) {
             // instruction descriptor: D = s32, A = B = unsigned 8-bit, both K-major, N = 64, M = 128
@@ -202,12 +203,15 @@ __global__ void __maxnreg__(224) group_bits_mma_kernel(const BitsMmaParams p) {
         __syncwarp();
     } else {
         // ================= EPILOGUE =================
-        const int q = warp - 4;                       // TMEM lane quarter: this warp may access lanes [32 q, 32 q + 32)
+        // warps 4-7 take accumulator columns 0-31, warps 8-11 columns 32-63; a warp may access TMEM lanes
+        // [32 q, 32 q + 32) with q = warp % 4
+        const int q = warp & 3, half = (warp - 4) >> 2;
         const int r = 32 * q + lane;                  // row of the tile = TMEM lane
         const int g = g0 + r;
-        double acc[BM_TN];
+        constexpr int HN = BM_TN / 2;
+        double acc[HN];
 #pragma unroll
-        for (int l = 0; l < BM_TN; ++l) acc[l] = 0.0;
+        for (int l = 0; l < HN; ++l) acc[l] = 0.0;
         double tw = 0.0;
         uint32_t tphase[2] = {0, 0};
         for (int it = 0; it < ntiles; ++it) {
@@ -215,40 +219,33 @@ __global__ void __maxnreg__(224) group_bits_mma_kernel(const BitsMmaParams p) {
             mbar_wait(&tfull_bar[a], tphase[a]);
             tphase[a] ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t v[32];
+            bm_tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)a * BM_TN + (uint32_t)half * HN, v);
+            // the accumulator stage is in registers: hand it back to the MMA warp before the FP64 work
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bm_arrive(&tempty_bar[a]);
             const double* m = meta + ((size_t)(it & 3) * BM_TM + r) * 2;
             const double w = m[0], xn = m[1];
             const int64_t pos = (r0 + it) * p.S + g;
-            if (w != 0.0 && blockIdx.y == 0 && pos < p.ES) tw += w;
-            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)a * BM_TN;
-            // two halves of 32 columns: 64 dot products + 64 FP64 accumulators would not fit the register file
+            if (w != 0.0) {
+                if (half == 0 && blockIdx.y == 0 && pos < p.ES) tw += w;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t v[32];
-                bm_tmem_ld32(taddr + 32u * h, v);
-                if (h == 1) {
-                    // the accumulator stage is in registers: hand it back to the MMA warp before the FP64 work
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) bm_arrive(&tempty_bar[a]);
-                }
-                if (w != 0.0) {
-#pragma unroll
-                    for (int l = 0; l < 32; ++l)
-                        acc[32 * h + l] = fma(tanimoto_value((double)(int)v[l], xn, zn_s[32 * h + l]), w, acc[32 * h + l]);
-                }
+                for (int l = 0; l < HN; ++l)
+                    acc[l] = fma(tanimoto_value((double)(int)v[l], xn, zn_s[half * HN + l]), w, acc[l]);
             }
         }
         if (g < p.S) {
-            double* out = p.out + ((int64_t)blockIdx.z * p.S + g) * p.L + l0;
+            double* out = p.out + ((int64_t)blockIdx.z * p.S + g) * p.L + l0 + half * HN;
 #pragma unroll
-            for (int l = 0; l < BM_TN; ++l)
-                if (l0 + l < p.L) out[l] = acc[l] * p.scale;
-            if (blockIdx.y == 0) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw;
+            for (int l = 0; l < HN; ++l)
+                if (l0 + half * HN + l < p.L) out[l] = acc[l] * p.scale;
+            if (half == 0 && blockIdx.y == 0) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) {
+    if (warp == BM_MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_base) : "memory");
     }
