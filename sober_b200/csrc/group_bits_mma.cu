@@ -130,44 +130,74 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
 
     if (warp < 4) {
         // ================= EXPANDERS =================
+        // Software pipeline over the tiles: the alive-list entry of tile it + 2 and the bit rows of tile it + 1 are in
+        // flight while tile it is expanded (the chain idx -> row -> words is two dependent L2 round trips; issued on
+        // demand it cost ~5000 cycles per tile and the tensor core sat idle).
         const int r = t;                              // row of the tile
         const int g = g0 + r;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int it = 0; it < ntiles; ++it) {
-            const int64_t e = r0 + it;
-            const int64_t pos = e * p.S + g;
-            const bool ok = g < p.S && pos >= p.pos0 && pos < hi;
-            int64_t row = 0;
-            double w = 0.0, xn = 0.0;
+        auto locate = [&](int it, int64_t& row, double& w, bool& ok) {
+            const int64_t pos = (r0 + it) * p.S + g;
+            ok = it < ntiles && g < p.S && pos >= p.pos0 && pos < hi;
+            row = 0;
+            w = 0.0;
             if (ok) {
                 const int64_t loc = pos - p.pos0;
                 row = p.idx ? (int64_t)__ldg(p.idx + loc) : loc;
                 w = p.mu ? __ldg(p.mu + loc) : 1.0;
-                xn = __ldg(p.xn + row * p.xn_stride);
             }
+        };
+        uint64_t cur[BM_MAXW], nxt[BM_MAXW];
+        auto fetch = [&](uint64_t (&dst)[BM_MAXW], int64_t row, bool ok) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(p.X + row * p.W);
+#pragma unroll
+            for (int wd = 0; wd < BM_MAXW; wd += 2) {
+                ulonglong2 v = make_ulonglong2(0ull, 0ull);
+                if (ok && wd < p.W) v = __ldg(src + wd / 2);
+                dst[wd] = v.x;
+                dst[wd + 1] = v.y;
+            }
+        };
+        int64_t row0_, row1_, row2_;
+        double w0_, w1_, w2_;
+        bool ok0_, ok1_, ok2_;
+        locate(0, row0_, w0_, ok0_);
+        locate(1, row1_, w1_, ok1_);
+        fetch(cur, row0_, ok0_);
+        double xn0_ = ok0_ ? __ldg(p.xn + row0_ * p.xn_stride) : 0.0;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            fetch(nxt, row1_, ok1_);                                     // bit rows of tile it + 1
+            const double xn1_ = ok1_ ? __ldg(p.xn + row1_ * p.xn_stride) : 0.0;
+            locate(it + 2, row2_, w2_, ok2_);                            // alive-list entry of tile it + 2
             double* m = meta + ((size_t)(it & 3) * BM_TM + r) * 2;
-            m[0] = w;
-            m[1] = xn;
-            const uint64_t* src = p.X + row * p.W;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1u);
-                unsigned char* dst = As + (size_t)stage * BM_TM * BM_KB;
+            m[0] = w0_;
+            m[1] = xn0_;
 #pragma unroll
-                for (int wd = 0; wd < BM_KB / 64; ++wd) {
-                    const uint64_t word = ok ? __ldg(src + kb * (BM_KB / 64) + wd) : 0ull;
+            for (int kb = 0; kb < BM_MAXW / 4; ++kb) {
+                if (kb < nkb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    unsigned char* dst = As + (size_t)stage * BM_TM * BM_KB;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t bits = (uint32_t)(word >> (16 * c)) & 0xffffu;
-                        const uint64_t lo = lut8[bits & 0xff], hh = lut8[bits >> 8];
-                        *reinterpret_cast<uint4*>(dst + ((size_t)(wd * 4 + c) * BM_TM + r) * 16) =
-                            make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hh, (uint32_t)(hh >> 32));
+                    for (int wd = 0; wd < BM_KB / 64; ++wd) {
+                        const uint64_t word = cur[kb * (BM_KB / 64) + wd];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t bits = (uint32_t)(word >> (16 * c)) & 0xffffu;
+                            const uint64_t lo = lut8[bits & 0xff], hh = lut8[bits >> 8];
+                            *reinterpret_cast<uint4*>(dst + ((size_t)(wd * 4 + c) * BM_TM + r) * 16) =
+                                make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hh, (uint32_t)(hh >> 32));
+                        }
                     }
+                    bm_fence_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
+                    bm_arrive(&full_bar[stage]);
+                    if (++stage == BM_STAGES) { stage = 0; phase ^= 1u; }
                 }
-                bm_fence_async();                     // generic-proxy writes -> visible to the tensor core (async proxy)
-                bm_arrive(&full_bar[stage]);
-                if (++stage == BM_STAGES) { stage = 0; phase ^= 1u; }
             }
+#pragma unroll
+            for (int wd = 0; wd < BM_MAXW; ++wd) cur[wd] = nxt[wd];
+            row0_ = row1_; w0_ = w1_; ok0_ = ok1_; xn0_ = xn1_;
+            row1_ = row2_; w1_ = w2_; ok1_ = ok2_;
         }
     } else if (warp == BM_MMA_WARP) {
         // ================= MMA ISSUER =================
@@ -232,7 +262,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
                 if (half == 0 && blockIdx.y == 0 && pos < p.ES) tw += w;
 #pragma unroll
                 for (int l = 0; l < HN; ++l)
-                    acc[l] = fma(tanimoto_value((double)(int)v[l], xn, zn_s[half * HN + l]), w, acc[l]);
+                    acc[l] = fma(tanimoto_value(__hiloint2double(0x43300000, (int)v[l]) - 4503599627370496.0, xn, zn_s[half * HN + l]), w, acc[l]);
             }
         }
         if (g < p.S) {
