@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
 #pragma unroll
             for (int kb = 0; kb < BM_MAXW / 4; ++kb) {
                 if (kb < nkb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    mbar_wait_sleep(&empty_bar[stage], phase ^ 1u);
                     unsigned char* dst = As + (size_t)stage * BM_TM * BM_KB;
 #pragma unroll
                     for (int wd = 0; wd < BM_KB / 64; ++wd) {
@@ -209,12 +209,12 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
             uint32_t phase = 0, tphase[2] = {0, 0};
             for (int it = 0; it < ntiles; ++it) {
                 const int acc = it & 1;
-                mbar_wait(&tempty_bar[acc], tphase[acc] ^ 1u);     // epilogue has drained this accumulator stage
+                mbar_wait_sleep(&tempty_bar[acc], tphase[acc] ^ 1u);     // epilogue has drained this accumulator stage
                 tphase[acc] ^= 1u;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * BM_TN;
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
+                    mbar_wait_sleep(&full_bar[stage], phase);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < BM_KB / 32; ++j) {
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
         uint32_t tphase[2] = {0, 0};
         for (int it = 0; it < ntiles; ++it) {
             const int a = it & 1;
-            mbar_wait(&tfull_bar[a], tphase[a]);
+            mbar_wait_sleep(&tfull_bar[a], tphase[a]);
             tphase[a] ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t v[32];
@@ -256,13 +256,13 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
             __syncwarp();
             if (lane == 0) bm_arrive(&tempty_bar[a]);
             const double* m = meta + ((size_t)(it & 3) * BM_TM + r) * 2;
-            const double w = m[0], xn = m[1];
+            const double w = m[0], exn = 1e-6 + m[1];
             const int64_t pos = (r0 + it) * p.S + g;
             if (w != 0.0) {
                 if (half == 0 && blockIdx.y == 0 && pos < p.ES) tw += w;
 #pragma unroll
                 for (int l = 0; l < HN; ++l)
-                    acc[l] = fma(tanimoto_value(__hiloint2double(0x43300000, (int)v[l]) - 4503599627370496.0, xn, zn_s[half * HN + l]), w, acc[l]);
+                    acc[l] = fma(tanimoto_bits_value(__hiloint2double(0x43300000, (int)v[l]) - 4503599627370496.0, exn, zn_s[half * HN + l]), w, acc[l]);
             }
         }
         if (g < p.S) {

@@ -27,6 +27,7 @@ for step in "$@"; do
     bench4)   TMO=600 TAILN=3 run bench_c4 python bench.py --workload c4 --steps 3 --warmup 2 --no-cpu-baseline ;;
     bench3)   TMO=600 TAILN=3 run bench_c3 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline ;;
     bitstime) TMO=300 TAILN=6 run bits_time python tools/bits_time.py ;;
+    ncubits)  TMO=600 run ncu_bits ncu --set full --clock-control none --import-source on -k regex:group_bits_mma -s 2 -c 1 -f -o $OUT/bitsprof python tools/bits_time.py ;;
     stagepar) TAILN=25 run stage_c2_parity python tools/stage_breakdown.py c2 parity ;;
     bench2)   TMO=600 TAILN=3 run bench_c2 python bench.py --steps 10 --warmup 3 ;;
     bench5)   TMO=600 TAILN=3 run bench_c5 python bench.py --workload c5 --steps 5 --warmup 2 --no-cpu-baseline ;;
