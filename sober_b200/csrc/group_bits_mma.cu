@@ -72,14 +72,26 @@ __device__ __forceinline__ void bm_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 bits -> 16 bytes of 0/1 without a table: a nibble n becomes (n * 0x00204081) & 0x01010101 (the four shifted copies
+// n, n << 7, n << 14, n << 21 do not overlap, bit j of n lands on bit 0 of byte j).  The first version used a 256-entry
+// byte -> 8-byte table in shared memory: its bank conflicts doubled the shared-memory wavefronts of the expanders, and
+// shared memory is what this kernel runs out of first (the tensor core reads its operands from it as well).
+__device__ __forceinline__ uint4 bm_expand16(uint32_t bits) {
+    uint4 o;
+    o.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+    o.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+    o.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+    o.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+    return o;
+}
+
 __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const BitsMmaParams p) {
     extern __shared__ __align__(128) unsigned char bm_smem[];
     const int K = p.W * 64;                          // K elements = bits
     const int nkb = K / BM_KB;                       // pipeline stages per tile
     unsigned char* Bs = bm_smem;                     // [K/16][64][16]
     unsigned char* As = Bs + (size_t)BM_TN * K;      // [stages][16][128][16]
-    uint64_t* lut8 = reinterpret_cast<uint64_t*>(As + (size_t)BM_STAGES * BM_TM * BM_KB);   // [256]
-    double* meta = reinterpret_cast<double*>(lut8 + 256);                                   // [4][128][2]  (w, |x|^2)
+    double* meta = reinterpret_cast<double*>(As + (size_t)BM_STAGES * BM_TM * BM_KB);        // [4][128][2]  (w, |x|^2)
     double* zn_s = meta + 4 * BM_TM * 2;                                                    // [64]
     __shared__ __align__(8) uint64_t full_bar[BM_STAGES], empty_bar[BM_STAGES], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_s;
@@ -97,28 +109,20 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
         mbar_fence_init();
     }
-    // byte -> 8 bytes of 0/1
-    for (int b = t; b < 256; b += BM_THREADS) {
-        uint64_t v = 0;
-        for (int i = 0; i < 8; ++i) v |= (uint64_t)((b >> i) & 1) << (8 * i);
-        lut8[b] = v;
-    }
     if (t < BM_TN) zn_s[t] = (l0 + t < p.L) ? p.zn[l0 + t] : 0.0;
     if (warp == BM_MMA_WARP) {                       // TMEM: 2 accumulator stages x 64 columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_addr(&tmem_base_s))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    __syncthreads();                                 // lut8 ready
+    __syncthreads();
     // resident landmark operand: chunk kc (16 K-elements) of landmark n at Bs[(kc * 64 + n) * 16]
     for (int c = t; c < BM_TN * (K / 16); c += BM_THREADS) {
         const int n = c % BM_TN, kc = c / BM_TN;
         uint4 val = make_uint4(0, 0, 0, 0);
         if (l0 + n < p.L) {
             const uint64_t word = __ldg(p.Z + (int64_t)(l0 + n) * p.W + (kc >> 2));
-            const uint32_t bits = (uint32_t)(word >> (16 * (kc & 3))) & 0xffffu;
-            const uint64_t lo = lut8[bits & 0xff], hh = lut8[bits >> 8];
-            val = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hh, (uint32_t)(hh >> 32));
+            val = bm_expand16((uint32_t)(word >> (16 * (kc & 3))) & 0xffffu);
         }
         *reinterpret_cast<uint4*>(Bs + ((size_t)kc * BM_TN + n) * 16) = val;
     }
@@ -183,10 +187,8 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
                         const uint64_t word = cur[kb * (BM_KB / 64) + wd];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            const uint32_t bits = (uint32_t)(word >> (16 * c)) & 0xffffu;
-                            const uint64_t lo = lut8[bits & 0xff], hh = lut8[bits >> 8];
                             *reinterpret_cast<uint4*>(dst + ((size_t)(wd * 4 + c) * BM_TM + r) * 16) =
-                                make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hh, (uint32_t)(hh >> 32));
+                                bm_expand16((uint32_t)(word >> (16 * c)) & 0xffffu);
                         }
                     }
                     bm_fence_async();                 // generic-proxy writes -> visible to the tensor core (async proxy)
