@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
                                                                   const int* __restrict__ piv,
                                                                   const double* __restrict__ Rt,
                                                                   const int* __restrict__ state, int S, int k, int t0,
-                                                                  int nb) {
+                                                                  int nb, int c_begin, int c_end) {
     extern __shared__ __align__(16) double su[];
     double* Us = su;                                // [CP_NB][CU_TI]
     double* Rs = su + CP_NB * CU_TI;                // [CU_TCOL][CP_NB + 1]
@@ -515,7 +515,8 @@ __global__ void __launch_bounds__(256, 2) car_panel_update_kernel(double* __rest
     if (*(volatile const int*)state != 0) return;
     const int t = threadIdx.x;
     const int i0 = blockIdx.x * CU_TI;
-    const int c0 = t0 + nb + blockIdx.y * CU_TCOL;
+    const int c0 = c_begin + blockIdx.y * CU_TCOL;   // columns [c_begin, c_end) of the trailing block
+    k = min(k, c_end);
     if (t < CU_TI) is_piv[t] = 0;
     for (int e = t; e < CP_NB * CU_TI; e += 256) {
         const int s = e / CU_TI, i = e % CU_TI;
@@ -610,6 +611,27 @@ static bool plan_panel(int S, int k, int nb_hint, PanelPlan* pl) {
     return true;
 }
 
+// helper stream + events of the lookahead, one set per device, created on first use and never destroyed
+struct Lookahead {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t solved = nullptr, rest_done = nullptr;
+    bool ok = false, tried = false;
+};
+static Lookahead& lookahead_for_device() {
+    static Lookahead table[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    Lookahead& la = table[dev];
+    if (!la.tried) {
+        la.tried = true;
+        la.ok = cudaStreamCreateWithFlags(&la.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.solved, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&la.rest_done, cudaEventDisableTiming) == cudaSuccess;
+        if (!la.ok) (void)cudaGetLastError();
+    }
+    return la;
+}
+
 }  // namespace sober
 
 using namespace sober;
@@ -659,6 +681,8 @@ extern "C" int sober_car_panel_profiled(double* basis, int32_t k, int32_t S, dou
             if (dev >= 0 && dev < 64) configured_upd[dev] = 1;
         }
     }
+    Lookahead& la = lookahead_for_device();
+    bool pending = false;
     for (int t0 = 0; t0 < k; t0 += pl.nb) {
         const int nb = (k - t0) < pl.nb ? (k - t0) : pl.nb;
         const bool trailing = t0 + nb < k;
@@ -681,16 +705,37 @@ extern "C" int sober_car_panel_profiled(double* basis, int32_t k, int32_t S, dou
         cfg.numAttrs = 1;
         SOBER_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, p));
         if (trailing) {
+            // LOOKAHEAD: only the next panel's columns must be up to date before the next panel kernel starts; the
+            // rest of the trailing update runs on a helper stream beside it (8 CTAs vs the remaining 140 SMs) and is
+            // joined before the next solve, which reads the pivot rows of ALL trailing columns.
             const int rest = k - (t0 + nb);
+            const size_t usm = (CP_NB * CU_TI + CU_TCOL * (CP_NB + 1)) * 8;
+            if (pending) {
+                SOBER_CUDA_CHECK(cudaStreamWaitEvent(st, la.rest_done, 0));
+                pending = false;
+            }
             car_panel_solve_kernel<<<(unsigned)ceil_div(rest, CS_WARPS), CS_WARPS * 32, 0, st>>>(basis, piv, lmat, state,
                                                                                                    S, k, t0, nb, Rt);
             SOBER_LAUNCH_CHECK("car_panel_solve");
-            dim3 grid((unsigned)ceil_div(S, CU_TI), (unsigned)ceil_div(rest, CU_TCOL));
-            car_panel_update_kernel<<<grid, 256, (CP_NB * CU_TI + CU_TCOL * (CP_NB + 1)) * 8, st>>>(basis, piv, Rt, state,
-                                                                                                       S, k, t0, nb);
+            const int first_end = (t0 + 2 * nb < k) ? t0 + 2 * nb : k;
+            dim3 grid1((unsigned)ceil_div(S, CU_TI), (unsigned)ceil_div(first_end - (t0 + nb), CU_TCOL));
+            if (first_end < k && la.ok) {
+                SOBER_CUDA_CHECK(cudaEventRecord(la.solved, st));
+                SOBER_CUDA_CHECK(cudaStreamWaitEvent(la.stream, la.solved, 0));
+                dim3 grid2((unsigned)ceil_div(S, CU_TI), (unsigned)ceil_div(k - first_end, CU_TCOL));
+                car_panel_update_kernel<<<grid2, 256, usm, la.stream>>>(basis, piv, Rt, state, S, k, t0, nb, first_end, k);
+                SOBER_LAUNCH_CHECK("car_panel_update");
+                SOBER_CUDA_CHECK(cudaEventRecord(la.rest_done, la.stream));
+                pending = true;
+                car_panel_update_kernel<<<grid1, 256, usm, st>>>(basis, piv, Rt, state, S, k, t0, nb, t0 + nb, first_end);
+            } else {
+                dim3 grid((unsigned)ceil_div(S, CU_TI), (unsigned)ceil_div(rest, CU_TCOL));
+                car_panel_update_kernel<<<grid, 256, usm, st>>>(basis, piv, Rt, state, S, k, t0, nb, t0 + nb, k);
+            }
             SOBER_LAUNCH_CHECK("car_panel_update");
         }
     }
+    if (pending) SOBER_CUDA_CHECK(cudaStreamWaitEvent(st, la.rest_done, 0));
     if (info) SOBER_CUDA_CHECK(cudaMemcpyAsync(info, state, 8, cudaMemcpyDeviceToDevice, st));
     return SOBER_OK;
 }

@@ -658,6 +658,18 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
         target = (int64_t)sm_count() * 8;
     }
     int64_t ns = ceil_div(target, gx * gy);
+    if (pl->bits_mma) {
+        // one CTA per SM: pick the split count whose last wave is fullest (3.46 waves would run as 4: -14 %)
+        const int64_t sms = sm_count();
+        int64_t best = ns;
+        double best_eff = 0.0;
+        for (int64_t c = ns; c <= ns + 6 && c <= rows; ++c) {
+            const int64_t ctas = gx * gy * c;
+            const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
+        }
+        ns = best;
+    }
     if (ns > rows) ns = rows;
     if (ns < 1) ns = 1;
     if (ns > 65535) ns = 65535;
