@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) popc_probe_kernel(int64_t iters, unsigned
         x += 0x9E3779B97F4A7C15ull;       // a new candidate word per trip (one 64-bit add per 4 word-ops)
     }
     const int s = (c0 + c1) + (c2 + c3);
-    if (s == -12345) sink[0] = s;  // never true: keeps the loop alive
+    if (s == 0x7ffffff1) sink[0] = s;  // practically never true (a NEGATIVE sentinel lets the compiler prove it false and drop the loop)
 }
 
 }  // namespace sober
