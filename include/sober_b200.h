@@ -220,6 +220,18 @@ int sober_car_panel(double* basis, int32_t k, int32_t S, double* mu, int32_t nb_
 int sober_car_panel_profiled(double* basis, int32_t k, int32_t S, double* mu, int32_t nb_hint, int32_t* info,
                              void* workspace, int64_t workspace_bytes, int64_t* prof, void* stream);
 
+/* Fused helpers of one Caratheodory step (csrc/car_helpers.cu), each replacing several library launches:
+ *  sober_car_prepare: out (S x (n+1), ldo) = column-normalised design matrix [1 | F / div] -- barycentres
+ *    (SOBER/_rchq.py:166; div may be NULL), ones column (:229) and the column scaling of the projector null space.
+ *  sober_car_summary: after the elimination.  If |delta|_F >= defect_limit (delta: ndelta doubles, the orthogonality
+ *    defect of the one-pass Cholesky-QR) or a weight is not finite, every weight becomes NaN; then
+ *    summary[i] = kept groups among 0..i, summary[S] = 1 if everything was fine, rank[i] = kept groups below i
+ *    (the bookkeeping of SOBER/_rchq.py:198-221 as the host reads it with one copy).  S <= 4096. */
+int sober_car_prepare(const double* F, int64_t ldf, const double* div, int32_t S, int32_t n, double* out, int64_t ldo,
+                      void* stream);
+int sober_car_summary(double* w, int32_t S, const double* delta, int64_t ndelta, double defect_limit, int32_t* summary,
+                      int32_t* rank, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * Weight update + compaction of the alive-list (SOBER/_rchq.py:198-221).
  *   For local position j (global p = pos0 + j):

@@ -117,10 +117,57 @@ def needs_retry(how, kept_count, dim, finite):
 _graphs = {}
 
 
-def _reduce_step(ops, feats, mass):
+_consts = {}
+
+
+def _step_constants(S, dim, device):
+    """-I and I (dim x dim) and [0 | I_k] (k x S): inputs of the addmm calls below, built once per shape."""
+    key = (S, dim, str(device))
+    c = _consts.get(key)
+    if c is None:
+        eye = torch.eye(dim, dtype=torch.float64, device=device)
+        e2t = torch.zeros((S - dim, S), dtype=torch.float64, device=device)
+        e2t[:, dim:] = torch.eye(S - dim, dtype=torch.float64, device=device)
+        c = _consts[key] = (-eye, eye, e2t)
+    return c
+
+
+def _reduce_step_fused(ops, feats, mass, divide):
+    """The fast-mode step with its bookkeeping folded into two hand-written kernels and the GEMM epilogues:
+    ``car_prepare`` (barycentres + ones column + column scaling), Gram / Cholesky / triangular solve, the Neumann-
+    corrected projector as three addmm calls (the -I, +I and [0 | I] terms ride on the GEMMs' beta operand), the
+    panelled elimination, ``car_summary`` (accuracy check of the projector, survivor counts and ranks).
+    14 launches instead of ~35; same arithmetic as ``projector_rows`` + ``_reduce_step``."""
+    from ._linalg import cholesky_upper, solve_right_upper
+    from ._settings import options
+    S, n = feats.shape
+    dim = n + 1
+    neg_eye, eye, e2t = _step_constants(S, dim, feats.device)
+    scaled = ops.car_prepare(feats, mass if divide else None)           # (S x dim), unit columns
+    r, _ = cholesky_upper(scaled.mH @ scaled)
+    qt = solve_right_upper(r, scaled)
+    delta = torch.addmm(neg_eye, qt.mH, qt)                             # Q^T Q - I
+    inv = torch.addmm(eye - delta, delta, delta)                        # I - Delta + Delta^2
+    rows = torch.addmm(e2t, qt[dim:, :] @ inv, qt.mH, alpha=-1.0)       # trailing k columns of I - Q (I + Delta)^-1 Q^T
+    out = mass.clone()
+    ops.car_panel(rows, out, nb_hint=options.car_panel_nb)
+    summary, rank = ops.car_summary(out, delta)
+    return out, None, summary, rank
+
+
+def _reduce_step(ops, feats, mass, divide=False):
     """feats (S x n), mass (S,) -> weights (S,), kept mask, host summary, exclusive rank of the kept.
+    ``divide``: feats are group SUMS, the barycentres are feats / mass (SOBER/_rchq.py:166).
     The host summary is int32 [inclusive cumulative count of kept groups (S) | all weights finite (1)]: one small
     device-to-host copy gives the host everything it needs (``KeepMap.from_summary``)."""
+    from ._settings import options
+    S, n = feats.shape
+    pfits = getattr(ops, "car_panel_fits", None)
+    if (hasattr(ops, "car_prepare") and options.car_kernel != "legacy" and pfits is not None and S > n + 1
+            and S <= 4096 and pfits(S, S - n - 1)):
+        return _reduce_step_fused(ops, feats, mass, divide)
+    if divide:
+        feats = feats / mass.unsqueeze(1)
     wfull = caratheodory(ops, feats, mass, "projector")
     kept = wfull > 0
     k32 = kept.to(torch.int32)
@@ -131,7 +178,7 @@ def _reduce_step(ops, feats, mass):
 
 
 class _ReduceGraph:
-    def __init__(self, ops, feats, mass):
+    def __init__(self, ops, feats, mass, divide=False):
         self.feats = torch.empty_like(feats)
         self.mass = torch.empty_like(mass)
         self.feats.copy_(feats)
@@ -141,7 +188,7 @@ class _ReduceGraph:
             torch.cuda.synchronize(feats.device)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-                self.out = _reduce_step(ops, self.feats, self.mass)
+                self.out = _reduce_step(ops, self.feats, self.mass, divide)
         finally:
             ops.timing = saved
         self.launches = 0
@@ -153,7 +200,7 @@ class _ReduceGraph:
         return self.out
 
 
-def reduce_step(ops, feats, mass, use_graph=True):
+def reduce_step(ops, feats, mass, use_graph=True, divide=False):
     """``_reduce_step``, replayed from a CUDA graph from the second call with the same shapes on (the outputs are then
     static buffers, valid until the next call).  Falls back to eager execution for good if the capture fails."""
     fits = getattr(ops, "car_cols_fits", None)
@@ -161,17 +208,17 @@ def reduce_step(ops, feats, mass, use_graph=True):
     pfits = getattr(ops, "car_panel_fits", None)
     if (not use_graph or not feats.is_cuda or fits is None or S <= n + 1
             or not (fits(S, S - n - 1) or (pfits is not None and pfits(S, S - n - 1)))):
-        return _reduce_step(ops, feats, mass)
-    key = (feats.device, S, n)
+        return _reduce_step(ops, feats, mass, divide)
+    key = (feats.device, S, n, divide)
     entry = _graphs.get(key)
     if entry is None:
         _graphs[key] = "seen"
-        return _reduce_step(ops, feats, mass)
+        return _reduce_step(ops, feats, mass, divide)
     from . import _linalg
     if entry == "seen":
         before, before_la = ops.launches, _linalg.launches
         try:
-            entry = _graphs[key] = _ReduceGraph(ops, feats, mass)
+            entry = _graphs[key] = _ReduceGraph(ops, feats, mass, divide)
             # kernels of ours inside the graph (bench.py's launch count): replays run them without passing the wrappers
             entry.launches = (ops.launches - before, _linalg.launches - before_la)
         except Exception as err:                        # capture unsupported here: stay eager, but say so once
@@ -180,10 +227,10 @@ def reduce_step(ops, feats, mass, use_graph=True):
                           % (str(err).splitlines()[0] if str(err) else type(err).__name__))
             _graphs[key] = "eager"
             ops.launches, _linalg.launches = before, before_la
-            return _reduce_step(ops, feats, mass)
+            return _reduce_step(ops, feats, mass, divide)
         ops.launches, _linalg.launches = before, before_la      # the capture itself executed nothing
     if entry == "eager":
-        return _reduce_step(ops, feats, mass)
+        return _reduce_step(ops, feats, mass, divide)
     ops.launches += entry.launches[0]
     _linalg.launches += entry.launches[1]
     t0 = ops._begin("car_step_graph")                   # the whole replay: null space + elimination + survivor ranks

@@ -348,6 +348,28 @@ class CudaOps:
         self.launches += 1 if (fits == 1 and not nb_hint) else 3 * ((k + nb - 1) // nb) - 2
         return info
 
+    def car_prepare(self, feats, div=None):
+        """Column-normalised design matrix [1 | feats / div] (S x (n + 1)) in one kernel."""
+        S, n = feats.shape
+        assert feats.stride(1) == 1
+        out = torch.empty((S, n + 1), dtype=torch.float64, device=self.device)
+        with self._guard():
+            check(self.lib.sober_car_prepare(_ptr(feats), feats.stride(0), _ptr(div), S, n, _ptr(out), out.stride(0),
+                                             self._stream()), "car_prepare")
+        self.launches += 1
+        return out
+
+    def car_summary(self, w, delta, defect_limit=1e-5):
+        """Poison ``w`` (in place) when the projector was inaccurate, then (summary int32 [S + 1], rank int32 [S])."""
+        S = w.numel()
+        summary = torch.empty(S + 1, dtype=torch.int32, device=self.device)
+        rank = torch.empty(S, dtype=torch.int32, device=self.device)
+        with self._guard():
+            check(self.lib.sober_car_summary(_ptr(w), S, _ptr(delta), 0 if delta is None else delta.numel(),
+                                             float(defect_limit), _ptr(summary), _ptr(rank), self._stream()), "car_summary")
+        self.launches += 1
+        return summary, rank
+
     # -- update + compaction ----------------------------------------------------------------------------------
     def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out,
                        rec=None, d=0):

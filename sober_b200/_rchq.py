@@ -477,18 +477,23 @@ class Recombiner:
                 if self.trace is not None:
                     self.trace("group", {"At": at.clone(), "totw": totw.clone(), "Xt_unnormalised": bary.clone(),
                                          "R": remaining, "E": E})
-                bary = bary / totw.unsqueeze(1)
                 design = None
+            graph_step = (design is None and self.nullspace is None and o.nullspace == "projector" and objs is None
+                          and self.trace is None)
+            if design is None and not graph_step:
+                bary = bary / totw.unsqueeze(1)
             clock.lap("tail+project")
             rank = keep = None
             n_design = (design.shape[1] if design is not None else bary.shape[1] + 1)
-            if (design is None and self.nullspace is None and o.nullspace == "projector" and objs is None
-                    and self.trace is None):
-                # the whole step (null space, elimination, survivor counts and ranks) as one CUDA-graph replay
-                wfull, kept, summary, rank = _car.reduce_step(ops, bary, totw, use_graph=o.graphs and o.stats is None)
+            if graph_step:
+                # the whole step (barycentres, null space, elimination, survivor counts and ranks) as one CUDA-graph replay
+                wfull, kept, summary, rank = _car.reduce_step(ops, bary, totw, use_graph=o.graphs and o.stats is None,
+                                                              divide=True)
                 summary = summary.tolist()                                               # the one host sync of the iteration
                 keep = KeepMap.from_summary(summary, S, ES)
                 retry = _car.needs_retry("projector", keep.K, n_design, bool(summary[S]))
+                if retry:
+                    bary = bary / totw.unsqueeze(1)
             else:
                 wfull = _car.caratheodory(ops, bary, totw, o.nullspace, self.nullspace, design=design)
                 kept = wfull > 0
