@@ -114,7 +114,8 @@ int sober_compact_nonzero(const double* mu, int64_t n, int32_t* idx_out, double*
  * workspace holds the per-split partial sums (deterministic two-stage reduction, no atomics).
  * variant: 0 = automatic (records -> register kernel, else tiled; SOBER_TANIMOTO_BITS with 256..1024-bit rows and at least
  *          2^20 pairs -> the tcgen05 kernel of csrc/group_bits_mma.cu), 1 = force the generic tiled kernel,
- *          4 = force the popcount kernel for SOBER_TANIMOTO_BITS.
+ *          4 = force the popcount kernel for SOBER_TANIMOTO_BITS, 5 = the first tcgen05 kernel (landmark tile in shared
+ *          memory instead of TMEM; kept for comparison).
  * ------------------------------------------------------------------------------------------------- */
 typedef struct sober_group_args {
     const double* X;

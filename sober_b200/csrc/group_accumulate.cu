@@ -36,7 +36,8 @@ struct BitsMmaParams {
     double scale;
 };
 bool bits_mma_supported(int W);
-int launch_bits_mma(const BitsMmaParams& p, dim3 grid, cudaStream_t st);
+int launch_bits_mma(const BitsMmaParams& p, dim3 grid, cudaStream_t st);    // v1: landmark tile resident in shared memory
+int launch_bits_mma2(const BitsMmaParams& p, dim3 grid, cudaStream_t st);   // v2: landmark tile resident in TMEM (A operand)
 
 struct GroupParams {
     const double* X;
@@ -608,6 +609,7 @@ static int bits_tl(int W) { return W <= 8 ? 4 : (W <= 16 ? 2 : 1); }
 
 struct Plan {
     bool bits_mma;     // bit-packed Tanimoto on the tensor cores (csrc/group_bits_mma.cu)
+    bool bits_mma_v1;  // variant 5: the first tcgen05 kernel (landmark tile in shared memory), kept for comparison
     bool records;
     bool bits;
     dim3 grid, block;
@@ -636,9 +638,10 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
     int64_t gx, gy, target;
     pl->bits_mma = a->family == SOBER_TANIMOTO_BITS && a->variant != 4 && bits_mma_supported((int)a->ldx) &&
                    a->n_local * (int64_t)a->L >= (1 << 20);
+    pl->bits_mma_v1 = a->variant == 5;
     if (pl->bits_mma) {
-        gx = ceil_div(a->S, 128);
-        gy = ceil_div(a->L, 64);
+        gx = ceil_div(a->S, pl->bits_mma_v1 ? 128 : 64);
+        gy = ceil_div(a->L, pl->bits_mma_v1 ? 64 : 128);
         pl->block = dim3(416);
         target = (int64_t)sm_count() * 3;    // one 167 KB CTA per SM, a few waves
     } else if (pl->bits) {
@@ -783,7 +786,7 @@ extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace
         q.n_local = a->n_local; q.pos0 = a->pos0; q.ES = a->ES; q.S = a->S; q.L = a->L; q.W = (int)a->ldx;
         q.out = p.out; q.totw_out = p.totw_out;
         q.row_begin = pl.row_begin; q.row_end = pl.row_end; q.rows_per_split = pl.rows_per_split; q.scale = p.scale;
-        const int rc = launch_bits_mma(q, pl.grid, st);
+        const int rc = pl.bits_mma_v1 ? launch_bits_mma(q, pl.grid, st) : launch_bits_mma2(q, pl.grid, st);
         if (rc != SOBER_OK) return rc;
         if (pl.nsplit > 1) {
             const int64_t n = SL > a->S ? SL : a->S;

@@ -283,12 +283,258 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
     }
 }
 
+// =====================================================================================================
+// Version 2: the LANDMARK tile lives in TMEM as the A operand of the MMA.
+//
+// Version 1 (above) runs out of shared memory first: per 128 x 64 tile the expanders store 128 KB and the tensor core
+// itself reads 192 KB of operands (A 4 KB + B 2 KB per MMA).  Here A = 128 landmarks x d bytes is expanded ONCE per CTA
+// into tensor memory (tcgen05.st: lane = landmark, one 32-bit column = 4 K-elements = one nibble of the bit row; 256
+// columns at d = 1024) and only the streamed candidate tile (B: 64 candidates x 256 K-elements per stage, 16 KB) passes
+// through shared memory: 64 KB stored + 64 KB read by the tensor core per 128 x 64 tile, and each candidate row is
+// expanded by L / 128 CTAs instead of L / 64.  The epilogue thread is now a LANDMARK (TMEM lane) and walks the tile's
+// candidates (accumulator columns): its 32 FP64 accumulators are the groups g0 + 32 h + j, stores to At are coalesced
+// along the landmarks.  TMEM: 256 columns A + 2 x 64 columns of int32 accumulators (512 allocated).
+// =====================================================================================================
+constexpr int B2_TN = 64;         // candidates (groups) per tile = accumulator columns
+constexpr int B2_TM = 128;        // landmarks per CTA = TMEM lanes
+constexpr int B2_STAGES = 4;
+constexpr int B2_META = 16;       // ring of per-tile candidate metadata: the epilogue lags the expanders by at most 7 tiles (d = 256)
+
+__device__ __forceinline__ void bm_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                 : "memory");
+}
+__device__ __forceinline__ void bm_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma2_kernel(const BitsMmaParams p) {
+    extern __shared__ __align__(128) unsigned char bm_smem[];
+    const int K = p.W * 64;
+    const int nkb = K / BM_KB;
+    unsigned char* Bs = bm_smem;                                                     // [stages][16][64][16]
+    double* meta = reinterpret_cast<double*>(Bs + (size_t)B2_STAGES * B2_TN * BM_KB); // [B2_META][64][2]  (w, eps + |x|^2)
+    __shared__ __align__(8) uint64_t full_bar[B2_STAGES], empty_bar[B2_STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int g0 = blockIdx.x * B2_TN;
+    const int l0 = blockIdx.y * B2_TM;
+    const int64_t r0 = p.row_begin + (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t r1 = min(p.row_end, r0 + p.rows_per_split);
+    const int64_t hi = p.pos0 + p.n_local;
+    const int ntiles = (int)max((int64_t)0, r1 - r0);
+
+    if (t == 0) {
+        for (int s = 0; s < B2_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        mbar_fence_init();
+    }
+    if (warp == BM_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_a = tmem_base;                 // columns [0, K / 4): the landmark operand
+    const uint32_t tmem_d = tmem_base + 256;           // columns [256, 384): two accumulator stages
+    // resident A operand: warps 4-7 (TMEM lane quarters 0-3), thread = landmark, 32 columns (= 32 nibbles) per store
+    if (warp >= 4 && warp < 8) {
+        const int q = warp & 3;
+        const int l = l0 + 32 * q + lane;
+        for (int c0 = 0; c0 < K / 4; c0 += 32) {       // 32 columns = 128 K-elements = 2 words
+            uint32_t v[32];
+            uint64_t w0 = 0ull, w1 = 0ull;
+            if (l < p.L) {
+                w0 = __ldg(p.Z + (int64_t)l * p.W + c0 / 16);
+                w1 = __ldg(p.Z + (int64_t)l * p.W + c0 / 16 + 1);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                v[j] = (((uint32_t)(w0 >> (4 * j)) & 15u) * 0x00204081u) & 0x01010101u;
+                v[16 + j] = (((uint32_t)(w1 >> (4 * j)) & 15u) * 0x00204081u) & 0x01010101u;
+            }
+            bm_tmem_st32(tmem_a + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    if (warp < 4) {
+        // ================= EXPANDERS: thread (row r, half h) expands words 2h, 2h + 1 of every 4-word K-block =================
+        const int r = t & 63, h = t >> 6;
+        const int g = g0 + r;
+        auto locate = [&](int it, int64_t& row, double& w, bool& ok) {
+            const int64_t pos = (r0 + it) * p.S + g;
+            ok = it < ntiles && g < p.S && pos >= p.pos0 && pos < hi;
+            row = 0;
+            w = 0.0;
+            if (ok) {
+                const int64_t loc = pos - p.pos0;
+                row = p.idx ? (int64_t)__ldg(p.idx + loc) : loc;
+                w = p.mu ? __ldg(p.mu + loc) : 1.0;
+            }
+        };
+        ulonglong2 cur[BM_MAXW / 4], nxt[BM_MAXW / 4];
+        auto fetch = [&](ulonglong2 (&dst)[BM_MAXW / 4], int64_t row, bool ok) {
+            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(p.X + row * p.W);
+#pragma unroll
+            for (int kb = 0; kb < BM_MAXW / 4; ++kb) {
+                dst[kb] = make_ulonglong2(0ull, 0ull);
+                if (ok && kb < nkb) dst[kb] = __ldg(src + kb * 2 + h);
+            }
+        };
+        int64_t row0_, row1_, row2_;
+        double w0_, w1_, w2_;
+        bool ok0_, ok1_, ok2_;
+        locate(0, row0_, w0_, ok0_);
+        locate(1, row1_, w1_, ok1_);
+        fetch(cur, row0_, ok0_);
+        double xn0_ = ok0_ ? __ldg(p.xn + row0_ * p.xn_stride) : 0.0;
+        double tw = 0.0;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            fetch(nxt, row1_, ok1_);
+            const double xn1_ = ok1_ ? __ldg(p.xn + row1_ * p.xn_stride) : 0.0;
+            locate(it + 2, row2_, w2_, ok2_);
+            if (h == 0) {
+                double* m = meta + ((size_t)(it & (B2_META - 1)) * B2_TN + r) * 2;
+                m[0] = w0_;
+                m[1] = 1e-6 + xn0_;
+                if ((r0 + it) * p.S + g < p.ES) tw += w0_;
+            }
+#pragma unroll
+            for (int kb = 0; kb < BM_MAXW / 4; ++kb) {
+                if (kb < nkb) {
+                    mbar_wait_sleep(&empty_bar[stage], phase ^ 1u);
+                    unsigned char* dst = Bs + (size_t)stage * B2_TN * BM_KB;
+#pragma unroll
+                    for (int wd = 0; wd < 2; ++wd) {
+                        const uint64_t word = wd == 0 ? cur[kb].x : cur[kb].y;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4*>(dst + ((size_t)((2 * h + wd) * 4 + c) * B2_TN + r) * 16) =
+                                bm_expand16((uint32_t)(word >> (16 * c)) & 0xffffu);
+                    }
+                    bm_fence_async();
+                    bm_arrive(&full_bar[stage]);
+                    if (++stage == B2_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+#pragma unroll
+            for (int kb = 0; kb < BM_MAXW / 4; ++kb) cur[kb] = nxt[kb];
+            row0_ = row1_; w0_ = w1_; ok0_ = ok1_; xn0_ = xn1_;
+            row1_ = row2_; w1_ = w2_; ok1_ = ok2_;
+        }
+        if (h == 0 && blockIdx.y == 0 && g < p.S) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw;
+    } else if (warp == BM_MMA_WARP) {
+        // ================= MMA ISSUER =================
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | ((uint32_t)(B2_TN >> 3) << 17) | ((uint32_t)(B2_TM >> 4) << 24);
+            const uint32_t b_base = smem_addr(Bs);
+            int stage = 0;
+            uint32_t phase = 0, tph = 0;
+            for (int it = 0; it < ntiles; ++it) {
+                const int acc = it & 1;
+                mbar_wait_sleep(&tempty_bar[acc], ((tph >> acc) & 1u) ^ 1u);
+                tph ^= 1u << acc;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_d + (uint32_t)acc * B2_TN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_sleep(&full_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < BM_KB / 32; ++j) {
+                        const uint64_t bdesc = bm_desc(b_base + (uint32_t)stage * B2_TN * BM_KB + (uint32_t)j * 2u * B2_TN * 16u,
+                                                       B2_TN * 16u, 128u);
+                        // A: 8 columns (32 K-elements) per MMA
+                        bm_mma_i8_ts(d_tmem, tmem_a + (uint32_t)(kb * (BM_KB / 4) + 8 * j), bdesc, idesc, (kb | j) != 0 ? 1u : 0u);
+                    }
+                    bm_commit(&empty_bar[stage]);
+                    if (++stage == B2_STAGES) { stage = 0; phase ^= 1u; }
+                }
+                bm_commit(&tfull_bar[acc]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= EPILOGUE: thread = landmark (TMEM lane), 32 candidates (columns) of the tile =================
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int l = l0 + 32 * q + lane;
+        constexpr int HN = B2_TN / 2;
+        const double zn = l < p.L ? __ldg(p.zn + l) : 0.0;
+        double acc[HN];
+#pragma unroll
+        for (int j = 0; j < HN; ++j) acc[j] = 0.0;
+        uint32_t tph = 0;
+        for (int it = 0; it < ntiles; ++it) {
+            const int a = it & 1;
+            mbar_wait_sleep(&tfull_bar[a], (tph >> a) & 1u);
+            tph ^= 1u << a;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t v[32];
+            bm_tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)a * B2_TN + (uint32_t)half * HN, v);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) bm_arrive(&tempty_bar[a]);
+            const double2* m = reinterpret_cast<const double2*>(meta + ((size_t)(it & (B2_META - 1)) * B2_TN + half * HN) * 2);
+#pragma unroll
+            for (int j = 0; j < HN; ++j) {
+                const double2 we = m[j];                  // (w, eps + |x|^2) of candidate j: broadcast load
+                acc[j] = fma(tanimoto_bits_value(__hiloint2double(0x43300000, (int)v[j]) - 4503599627370496.0, we.y, zn),
+                             we.x, acc[j]);
+            }
+        }
+        if (l < p.L) {
+#pragma unroll
+            for (int j = 0; j < HN; ++j) {
+                const int g = g0 + half * HN + j;
+                if (g < p.S) p.out[((int64_t)blockIdx.z * p.S + g) * p.L + l] = acc[j] * p.scale;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == BM_MMA_WARP) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+size_t bits_mma2_smem() { return (size_t)B2_STAGES * B2_TN * BM_KB + (size_t)B2_META * B2_TN * 2 * 8 + 128; }
+
 size_t bits_mma_smem(int W) {
     const size_t K = (size_t)W * 64;
     return (size_t)BM_TN * K + (size_t)BM_STAGES * BM_TM * BM_KB + 256 * 8 + 4 * BM_TM * 2 * 8 + BM_TN * 8 + 128;
 }
 
 bool bits_mma_supported(int W) { return W >= 4 && W <= BM_MAXW && W % 4 == 0; }
+
+int launch_bits_mma2(const BitsMmaParams& p, dim3 grid, cudaStream_t st) {
+    const size_t smem = bits_mma2_smem();
+    static int configured[64] = {};
+    int dev = 0;
+    SOBER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        SOBER_CUDA_CHECK(cudaFuncSetAttribute(group_bits_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) configured[dev] = 1;
+    }
+    group_bits_mma2_kernel<<<grid, BM_THREADS, smem, st>>>(p);
+    SOBER_LAUNCH_CHECK("group_bits_mma2");
+    return SOBER_OK;
+}
 
 int launch_bits_mma(const BitsMmaParams& p, dim3 grid, cudaStream_t st) {
     const size_t smem = bits_mma_smem(p.W);

@@ -36,13 +36,14 @@ def test_mma_gram_bitwise_equals_popcount_kernel(ops, cuda_device, d, density):
     Z = X[torch.randperm(n, generator=g)[:L].to(cuda_device)].clone()
     pts, lm = tables(ops, X, Z)
     out = {}
-    for variant in (0, 4):
+    for variant in (0, 4, 5):       # 0: landmark tile in TMEM, 5: landmark tile in shared memory, 4: popcount
         ops.variant = variant
         try:
             out[variant], _ = ops.group_accumulate(pts, lm, None, None, n, 0, 0, n)
         finally:
             ops.variant = 0
     assert torch.equal(out[0], out[4])
+    assert torch.equal(out[5], out[4])
     kern = ok.Kernel(ok.BareModel(ok.make_kernel("tanimoto", 1.0, 1.7).to(cuda_device)), mode="kernel")
     want = kern(Z, X).T
     assert float((out[0] - want).abs().max() / want.abs().max()) < 1e-13
@@ -60,13 +61,14 @@ def test_mma_group_sums_match_popcount_kernel(ops, cuda_device, n_local, S, pos0
     pts, lm = tables(ops, X, Z)
     ES = ((pos0 + n_local) // S) * S - S                                               # a remainder of more than one row
     out = {}
-    for variant in (0, 4):
+    for variant in (0, 4, 5):
         ops.variant = variant
         try:
             out[variant] = ops.group_accumulate(pts, lm, idx, mu, n_local, pos0, ES, S)
         finally:
             ops.variant = 0
-    at0, tw0 = out[0]
     at4, tw4 = out[4]
-    assert float((at0 - at4).abs().max() / at4.abs().max()) < 1e-13
-    assert float((tw0 - tw4).abs().max() / tw4.abs().max()) < 1e-13
+    for v in (0, 5):
+        at, tw = out[v]
+        assert float((at - at4).abs().max() / at4.abs().max()) < 1e-13
+        assert float((tw - tw4).abs().max() / tw4.abs().max()) < 1e-13

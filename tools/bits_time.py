@@ -1,5 +1,6 @@
 """K1 on bit-packed 1024-bit fingerprints (C4 shape: L = 1000 landmarks, S = 1000 groups): the tcgen05 kernel
-(csrc/group_bits_mma.cu, variant 0) against the popcount kernel (variant 4)."""
+(csrc/group_bits_mma.cu; variant 0 = landmark tile in TMEM, variant 5 = in shared memory) against the popcount kernel
+(variant 4)."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sober_b200 import _lib
@@ -17,7 +18,7 @@ for (N, L, S, d) in [(1_000_000, 1000, 1000, 1024), (250_000, 1000, 1000, 1024),
     lm = LandmarkTable(zw, zp, _lib.TANIMOTO_BITS, 1.0, d=d)
     E = N // S
     res = {}
-    for variant in (0, 4):
+    for variant in (0, 5, 4):
         ops.variant = variant
         for _ in range(2):
             at, tw = ops.group_accumulate(pts, lm, None, mu, N, 0, E * S, S)
@@ -29,8 +30,9 @@ for (N, L, S, d) in [(1_000_000, 1000, 1000, 1024), (250_000, 1000, 1000, 1024),
         b.record(); torch.cuda.synchronize()
         res[variant] = (a.elapsed_time(b) / 3, at.clone())
     ops.variant = 0
-    ms0, ms4 = res[0][0], res[4][0]
+    ms0, ms5, ms4 = res[0][0], res[5][0], res[4][0]
     pairs = N * L
-    print("N=%8d L=%4d S=%4d d=%4d: tcgen05 %.3f ms (%.1f G pairs/s, %.0f TOP/s int8) | popcount %.3f ms (%.1f G pairs/s) | x%.1f | max rel diff %.1e"
-          % (N, L, S, d, ms0, pairs / ms0 / 1e6, 2 * pairs * d / ms0 / 1e9, ms4, pairs / ms4 / 1e6, ms4 / ms0,
-             float((res[0][1] - res[4][1]).abs().max() / res[4][1].abs().max())))
+    print("N=%8d L=%4d S=%4d d=%4d: tcgen05/TMEM-A %.3f ms (%.1f G pairs/s, %.0f TOP/s int8) | tcgen05/smem-A %.3f ms | popcount %.3f ms (%.1f G pairs/s) | x%.1f | max rel diff %.1e %.1e"
+          % (N, L, S, d, ms0, pairs / ms0 / 1e6, 2 * pairs * d / ms0 / 1e9, ms5, ms4, pairs / ms4 / 1e6, ms4 / ms0,
+             float((res[0][1] - res[4][1]).abs().max() / res[4][1].abs().max()),
+             float((res[5][1] - res[4][1]).abs().max() / res[4][1].abs().max())))
