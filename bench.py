@@ -580,14 +580,15 @@ def main():
         peak = 2.0 * bf16 if bf16 else 4500.0
         rate = 2.0 * k1_pairs * d / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else None
         roofline = {
-            "kernel": "group_accumulate (K1, bit-packed Tanimoto on tcgen05: kind::i8 MMA over fingerprints expanded to 0/1 bytes "
-                      "in shared memory, int32 accumulators in TMEM, FP64 ratio epilogue)",
+            "kernel": "group_accumulate (K1, bit-packed Tanimoto on tcgen05: kind::i8 MMA, landmark tile resident in TMEM as the A "
+                      "operand, candidate fingerprints expanded to 0/1 bytes in shared memory, int32 accumulators in TMEM, FP64 "
+                      "ratio epilogue)",
             "bound": "tensor", "achieved": rate, "peak": peak, "unit": "TOP/s (int8, 2 ops per bit pair)",
             "frac": (rate / peak) if rate else None, "traffic": None,
             "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops (int8 issues at twice the bf16 rate; no measured int8 entry)"
                             if bf16 else "nominal 4.5 POP/s dense int8"),
-            "note": "the kernel is bound by its FP64 epilogue and the bit expansion (shared-memory bandwidth), not by the MMA: "
-                    "see profiles/r02_bits_tcgen05.txt; the popcount kernel it replaces ran at 122 G pairs/s",
+            "note": "the kernel is bound by instruction issue of the bit expansion and the FP64 epilogue, not by the MMA "
+                    "(tensor pipe 31 % active): see profiles/r02_bits_tcgen05.txt; the popcount kernel it replaces ran at 122 G pairs/s",
             "pairs_per_step": k1_pairs / max(args.steps, 1), "pairs_per_second": k1_pairs / (k1_ms * 1e-3) if k1_ms > 0 else None,
             "launches": k1_calls, "ms_per_step": k1_ms / max(args.steps, 1), "share_of_step": share,
         }

@@ -178,17 +178,16 @@ __device__ __forceinline__ double tanimoto_value(double dot, double xn, double z
     return fmax(v, 0.0);
 }
 
-// Tanimoto on bit-packed rows: dot, |x|^2, |z|^2 are exact small integers with dot <= min(|x|^2, |z|^2), so the ratio is
-// >= 0 without a clamp and the denominator >= eps; exn = eps + |x|^2.  MUFU seed (2^-22) + two Newton steps: <= 3 ulp.
-// Shared by the popcount kernel and the tcgen05 kernel, whose Grams are therefore bitwise equal.
-__device__ __forceinline__ double tanimoto_bits_value(double dot, double exn, double zn) {
-    const double den = exn + (zn - dot);
+// Tanimoto on bit-packed rows: dot, |x|^2, |z|^2 are exact small integers with dot <= min(|x|^2, |z|^2), so
+// m = |x|^2 + |z|^2 - dot is an exact integer >= 0 and the ratio (dot + eps) / (m + eps) needs no clamp.  zne = |z|^2 + eps
+// is formed once per landmark.  Reciprocal: MUFU seed + ONE Newton step, 3.3e-13 measured against the oracle's division,
+// far below the 1e-10 the kernel matrix has to match to; the second step cost 2 of the 10 FP64 instructions per
+// pair that bound the tcgen05 epilogue.  Shared by the popcount kernel and the tcgen05 kernels: their Grams are bitwise equal.
+__device__ __forceinline__ double tanimoto_bits_value(double dot, double xn, double zne) {
+    const double den = (xn + zne) - dot;
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(den));
-    double e = fma(-den, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-den, y, 1.0);
-    y = fma(y, e, y);
+    y = fma(y, fma(-den, y, 1.0), y);
     return (dot + 1e-6) * y;
 }
 
@@ -230,6 +229,22 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity), "r"(20000u)
         : "memory");
+}
+// the same with a back-off: a failed try_wait puts the warp to sleep instead of polling the barrier's shared-memory word
+// (16 epilogue warps polling one barrier were a quarter of the shared-memory wavefronts of the tcgen05 Tanimoto kernel)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns = 64) {
+    uint32_t done;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

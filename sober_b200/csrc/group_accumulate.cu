@@ -529,10 +529,9 @@ __global__ void __launch_bounds__(256) group_bits_kernel(const GroupParams p) {
                         for (int i = 0; i < TL; ++i) cnt[i] += __popcll(LUT ? (xw ^ zb[i][w]) : (xw & zb[i][w]));
                     }
                     const double xn = s_xn[r][j], wgt = s_w[r][j];
-                    const double exn = 1e-6 + xn;
 #pragma unroll
                     for (int i = 0; i < TL; ++i) {
-                        const double kv = LUT ? lut_s[cnt[i]] : tanimoto_bits_value((double)cnt[i], exn, zn[i]);
+                        const double kv = LUT ? lut_s[cnt[i]] : tanimoto_bits_value((double)cnt[i], xn, zn[i] + 1e-6);
                         acc[i][j] = fma(kv, wgt, acc[i][j]);
                     }
                 }

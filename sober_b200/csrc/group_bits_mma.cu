@@ -258,13 +258,13 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
             __syncwarp();
             if (lane == 0) bm_arrive(&tempty_bar[a]);
             const double* m = meta + ((size_t)(it & 3) * BM_TM + r) * 2;
-            const double w = m[0], exn = 1e-6 + m[1];
+            const double w = m[0], exn = m[1];
             const int64_t pos = (r0 + it) * p.S + g;
             if (w != 0.0) {
                 if (half == 0 && blockIdx.y == 0 && pos < p.ES) tw += w;
 #pragma unroll
                 for (int l = 0; l < HN; ++l)
-                    acc[l] = fma(tanimoto_bits_value(__hiloint2double(0x43300000, (int)v[l]) - 4503599627370496.0, exn, zn_s[half * HN + l]), w, acc[l]);
+                    acc[l] = fma(tanimoto_bits_value(__hiloint2double(0x43300000, (int)v[l]) - 4503599627370496.0, exn, zn_s[half * HN + l] + 1e-6), w, acc[l]);
             }
         }
         if (g < p.S) {
@@ -297,8 +297,46 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
 // =====================================================================================================
 constexpr int B2_TN = 64;         // candidates (groups) per tile = accumulator columns
 constexpr int B2_TM = 128;        // landmarks per CTA = TMEM lanes
-constexpr int B2_STAGES = 4;
+constexpr int B2_SLOTS = 2;                     // operand slots: one tile's K-blocks each (64 rows x d bytes, <= 64 KB)
+constexpr int B2_SLOT_BYTES = B2_TN * BM_MAXW * 64;
 constexpr int B2_META = 16;       // ring of per-tile candidate metadata: the epilogue lags the expanders by at most 7 tiles (d = 256)
+// Epilogue warps: B2_EG column groups per TMEM lane quarter.  One warp issues an FP64 instruction only every ~13 cycles
+// (measured: 2 epilogue warps per scheduler left the FP64 pipe at 30 % with every warp stalled on it), so the epilogue
+// wants thread-level parallelism: 4 warps per scheduler, 16 candidates (accumulator columns) of the tile each.
+constexpr int B2_EG = 4;
+constexpr int B2_HN = B2_TN / B2_EG;
+constexpr int B2_EPI_WARPS = 4 * B2_EG;
+#ifndef SOBER_B2_XW
+#define SOBER_B2_XW 8
+#endif
+constexpr int B2_XW = SOBER_B2_XW;              // expander warps (a multiple of 4, so the epilogue warps keep warp % 4 = lane quarter)
+constexpr int B2_XP = B2_XW * 32 / B2_TN;       // expander threads per candidate row
+constexpr int B2_WPT = 4 / B2_XP;               // 64-bit words per expander thread and 256-bit K-block
+constexpr int B2_MMA_WARP = B2_XW + B2_EPI_WARPS;
+constexpr int B2_DEPTH = 3;                     // tiles of global-load lookahead in the loaders
+constexpr int B2_RING = 8;                      // staging slots for raw words / weights / popcounts (> B2_DEPTH + 1, power of 2)
+constexpr int B2_IRING = 8;                     // staging slots for alive-list entries (>= 2 B2_DEPTH + 1, power of 2)
+constexpr int B2_THREADS = (B2_MMA_WARP + 1 + B2_TN / 32) * 32;   // + the loader warps (one lane per candidate row)
+
+__device__ __forceinline__ void bm_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool bm_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+template <int BYTES>
+__device__ __forceinline__ void bm_cp_async(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_addr(dst_smem)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void bm_tmem_ldn(uint32_t taddr, uint32_t (&v)[16]) { bm_tmem_ld16(taddr, v); }
+__device__ __forceinline__ void bm_tmem_ldn(uint32_t taddr, uint32_t (&v)[32]) { bm_tmem_ld32(taddr, v); }
 
 __device__ __forceinline__ void bm_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
@@ -314,29 +352,40 @@ __device__ __forceinline__ void bm_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "memory");
 }
 
-__global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma2_kernel(const BitsMmaParams p) {
+__global__ void __launch_bounds__(B2_THREADS, 1) group_bits_mma2_kernel(const BitsMmaParams p) {
     extern __shared__ __align__(128) unsigned char bm_smem[];
     const int K = p.W * 64;
     const int nkb = K / BM_KB;
-    unsigned char* Bs = bm_smem;                                                     // [stages][16][64][16]
-    double* meta = reinterpret_cast<double*>(Bs + (size_t)B2_STAGES * B2_TN * BM_KB); // [B2_META][64][2]  (w, eps + |x|^2)
-    __shared__ __align__(8) uint64_t full_bar[B2_STAGES], empty_bar[B2_STAGES], tfull_bar[2], tempty_bar[2];
+    unsigned char* Bs = bm_smem;                                                     // [slots][4 K-blocks][16][64][16]
+    double* meta = reinterpret_cast<double*>(Bs + (size_t)B2_SLOTS * B2_SLOT_BYTES);  // [B2_META][64][2]  (w, |x|^2)
+    uint64_t* raw = reinterpret_cast<uint64_t*>(meta + (size_t)B2_META * B2_TN * 2); // [B2_RING][BM_MAXW][64] staged words
+    double* wraw = reinterpret_cast<double*>(raw + (size_t)B2_RING * BM_MAXW * B2_TN);   // [B2_RING][64]
+    double* xraw = wraw + B2_RING * B2_TN;                                           // [B2_RING][64]
+    int* irow = reinterpret_cast<int*>(xraw + B2_RING * B2_TN);                      // [B2_IRING][64]
+    __shared__ __align__(8) uint64_t full_bar[B2_SLOTS], empty_bar[B2_SLOTS], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t raw_full[B2_RING], raw_empty[B2_RING];
     __shared__ uint32_t tmem_base_s;
 
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x, lane = t & 31, warp = __shfl_sync(0xffffffffu, t >> 5, 0);   // provably warp-uniform
     const int g0 = blockIdx.x * B2_TN;
     const int l0 = blockIdx.y * B2_TM;
     const int64_t r0 = p.row_begin + (int64_t)blockIdx.z * p.rows_per_split;
     const int64_t r1 = min(p.row_end, r0 + p.rows_per_split);
     const int64_t hi = p.pos0 + p.n_local;
     const int ntiles = (int)max((int64_t)0, r1 - r0);
+    auto alive_at = [&](int it, int g, int64_t& loc) {
+        const int64_t pos = (r0 + it) * p.S + g;
+        loc = pos - p.pos0;
+        return it >= 0 && it < ntiles && g < p.S && pos >= p.pos0 && pos < hi;
+    };
 
     if (t == 0) {
-        for (int s = 0; s < B2_STAGES; ++s) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
+        for (int s = 0; s < B2_SLOTS; ++s) { mbar_init(&full_bar[s], B2_XW * 32); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], B2_EPI_WARPS); }
+        for (int s = 0; s < B2_RING; ++s) { mbar_init(&raw_full[s], B2_TN); mbar_init(&raw_empty[s], B2_XW); }
         mbar_fence_init();
     }
-    if (warp == BM_MMA_WARP) {
+    if (warp == B2_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(&tmem_base_s))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -344,11 +393,11 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma2_kernel(const Bi
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
     const uint32_t tmem_a = tmem_base;                 // columns [0, K / 4): the landmark operand
     const uint32_t tmem_d = tmem_base + 256;           // columns [256, 384): two accumulator stages
-    // resident A operand: warps 4-7 (TMEM lane quarters 0-3), thread = landmark, 32 columns (= 32 nibbles) per store
-    if (warp >= 4 && warp < 8) {
+    // resident A operand: 4 epilogue warps (TMEM lane quarters 0-3), thread = landmark, 32 columns (= 32 nibbles) per store
+    if (warp >= B2_XW && warp < B2_XW + 4) {
         const int q = warp & 3;
         const int l = l0 + 32 * q + lane;
         for (int c0 = 0; c0 < K / 4; c0 += 32) {       // 32 columns = 128 K-elements = 2 words
@@ -371,149 +420,155 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma2_kernel(const Bi
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    if (warp < 4) {
-        // ================= EXPANDERS: thread (row r, half h) expands words 2h, 2h + 1 of every 4-word K-block =================
-        const int r = t & 63, h = t >> 6;
+    if (warp > B2_MMA_WARP) {
+        // ================= LOADERS: lane = candidate row of the tile =================
+        // Global latency stays out of everybody else's loop: cp.async into staging slots, B2_DEPTH tiles ahead for the
+        // fingerprint words / weight / popcount and 2 B2_DEPTH tiles ahead for the alive-list entry they depend on.  The
+        // loaders never fence (the expanders' fence.proxy.async compiles to a MEMBAR that would wait for every copy in
+        // flight), and hand a slot over with an mbarrier once cp.async.wait_group says it has landed.
+        constexpr int D = B2_DEPTH;
+        const int r = t - (B2_MMA_WARP + 1) * 32;
         const int g = g0 + r;
-        auto locate = [&](int it, int64_t& row, double& w, bool& ok) {
-            const int64_t pos = (r0 + it) * p.S + g;
-            ok = it < ntiles && g < p.S && pos >= p.pos0 && pos < hi;
-            row = 0;
-            w = 0.0;
-            if (ok) {
-                const int64_t loc = pos - p.pos0;
-                row = p.idx ? (int64_t)__ldg(p.idx + loc) : loc;
-                w = p.mu ? __ldg(p.mu + loc) : 1.0;
-            }
-        };
-        ulonglong2 cur[BM_MAXW / 4], nxt[BM_MAXW / 4];
-        auto fetch = [&](ulonglong2 (&dst)[BM_MAXW / 4], int64_t row, bool ok) {
-            const ulonglong2* src = reinterpret_cast<const ulonglong2*>(p.X + row * p.W);
-#pragma unroll
-            for (int kb = 0; kb < BM_MAXW / 4; ++kb) {
-                dst[kb] = make_ulonglong2(0ull, 0ull);
-                if (ok && kb < nkb) dst[kb] = __ldg(src + kb * 2 + h);
-            }
-        };
-        int64_t row0_, row1_, row2_;
-        double w0_, w1_, w2_;
-        bool ok0_, ok1_, ok2_;
-        locate(0, row0_, w0_, ok0_);
-        locate(1, row1_, w1_, ok1_);
-        fetch(cur, row0_, ok0_);
-        double xn0_ = ok0_ ? __ldg(p.xn + row0_ * p.xn_stride) : 0.0;
         double tw = 0.0;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int it = 0; it < ntiles; ++it) {
-            fetch(nxt, row1_, ok1_);
-            const double xn1_ = ok1_ ? __ldg(p.xn + row1_ * p.xn_stride) : 0.0;
-            locate(it + 2, row2_, w2_, ok2_);
-            if (h == 0) {
-                double* m = meta + ((size_t)(it & (B2_META - 1)) * B2_TN + r) * 2;
-                m[0] = w0_;
-                m[1] = 1e-6 + xn0_;
-                if ((r0 + it) * p.S + g < p.ES) tw += w0_;
+        for (int it = -2 * D; it < ntiles; ++it) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+            int64_t loc;
+            if (p.idx && alive_at(it + 2 * D, g, loc)) bm_cp_async<4>(&irow[((it + 2 * D) & (B2_IRING - 1)) * B2_TN + r], p.idx + loc);
+            const int tb = it + D;
+            if (tb >= 0 && tb < ntiles) {
+                const int slot = tb & (B2_RING - 1);
+                mbar_wait_backoff(&raw_empty[slot], ((uint32_t)(tb / B2_RING) & 1u) ^ 1u, 256);
+                if (alive_at(tb, g, loc)) {
+                    const int64_t row = p.idx ? (int64_t)irow[(tb & (B2_IRING - 1)) * B2_TN + r] : loc;
+                    const uint64_t* src = p.X + row * p.W;
+                    for (int w = 0; w < p.W; ++w) bm_cp_async<8>(&raw[((size_t)slot * BM_MAXW + w) * B2_TN + r], src + w);
+                    if (p.mu) bm_cp_async<8>(&wraw[slot * B2_TN + r], p.mu + loc);
+                    bm_cp_async<8>(&xraw[slot * B2_TN + r], p.xn + row * p.xn_stride);
+                }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (it < 0) continue;
+            const bool ok = alive_at(it, g, loc);
+            const int slot = it & (B2_RING - 1);
+            const double w = ok ? (p.mu ? wraw[slot * B2_TN + r] : 1.0) : 0.0;
+            double* m = meta + ((size_t)(it & (B2_META - 1)) * B2_TN + r) * 2;
+            m[0] = w;
+            m[1] = ok ? xraw[slot * B2_TN + r] : 0.0;
+            if ((r0 + it) * p.S + g < p.ES) tw += w;
+            bm_arrive(&raw_full[slot]);
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (blockIdx.y == 0 && g < p.S) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw;
+    } else if (warp < B2_XW) {
+        // ================= EXPANDERS: thread (row r, part h) expands word h of each of the tile's 4-word K-blocks =================
+        // ONE fence.proxy.async per tile and thread (it costs a MEMBAR.ALL.CTA): the tile's K-blocks go to one of two
+        // 64 KB operand slots, so the MMA warp works on a slot while the next is being filled.
+        const int r = t & (B2_TN - 1), h = t / B2_TN;
+        const int g = g0 + r;
+        for (int it = 0; it < ntiles; ++it) {
+            const int slot = it & (B2_RING - 1);
+            int64_t loc;
+            const bool ok = alive_at(it, g, loc);
+            mbar_wait_backoff(&raw_full[slot], (uint32_t)(it / B2_RING) & 1u, 128);
+            uint64_t word[BM_MAXW / 4][B2_WPT];
+#pragma unroll
+            for (int kb = 0; kb < BM_MAXW / 4; ++kb)
+#pragma unroll
+                for (int wd = 0; wd < B2_WPT; ++wd)
+                    word[kb][wd] = (ok && kb < nkb) ? raw[((size_t)slot * BM_MAXW + kb * 4 + h * B2_WPT + wd) * B2_TN + r] : 0ull;
+            __syncwarp();
+            if (lane == 0) bm_arrive(&raw_empty[slot]);
+            const int bs = it & (B2_SLOTS - 1);
+            mbar_wait_backoff(&empty_bar[bs], ((uint32_t)(it / B2_SLOTS) & 1u) ^ 1u, 128);
+            unsigned char* dst = Bs + (size_t)bs * B2_SLOT_BYTES;
 #pragma unroll
             for (int kb = 0; kb < BM_MAXW / 4; ++kb) {
                 if (kb < nkb) {
-                    mbar_wait_sleep(&empty_bar[stage], phase ^ 1u);
-                    unsigned char* dst = Bs + (size_t)stage * B2_TN * BM_KB;
 #pragma unroll
-                    for (int wd = 0; wd < 2; ++wd) {
-                        const uint64_t word = wd == 0 ? cur[kb].x : cur[kb].y;
+                    for (int wd = 0; wd < B2_WPT; ++wd) {
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
-                            *reinterpret_cast<uint4*>(dst + ((size_t)((2 * h + wd) * 4 + c) * B2_TN + r) * 16) =
-                                bm_expand16((uint32_t)(word >> (16 * c)) & 0xffffu);
+                            *reinterpret_cast<uint4*>(dst + (size_t)kb * B2_TN * BM_KB +
+                                                      ((size_t)((B2_WPT * h + wd) * 4 + c) * B2_TN + r) * 16) =
+                                bm_expand16((uint32_t)(word[kb][wd] >> (16 * c)) & 0xffffu);
                     }
-                    bm_fence_async();
-                    bm_arrive(&full_bar[stage]);
-                    if (++stage == B2_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
-#pragma unroll
-            for (int kb = 0; kb < BM_MAXW / 4; ++kb) cur[kb] = nxt[kb];
-            row0_ = row1_; w0_ = w1_; ok0_ = ok1_; xn0_ = xn1_;
-            row1_ = row2_; w1_ = w2_; ok1_ = ok2_;
+            bm_fence_async();
+            bm_arrive(&full_bar[bs]);
         }
-        if (h == 0 && blockIdx.y == 0 && g < p.S) p.totw_out[(int64_t)blockIdx.z * p.S + g] = tw;
-    } else if (warp == BM_MMA_WARP) {
+    } else if (warp == B2_MMA_WARP) {
         // ================= MMA ISSUER =================
-        if (lane == 0) {
-            const uint32_t idesc = (2u << 4) | ((uint32_t)(B2_TN >> 3) << 17) | ((uint32_t)(B2_TM >> 4) << 24);
-            const uint32_t b_base = smem_addr(Bs);
-            int stage = 0;
-            uint32_t phase = 0, tph = 0;
-            for (int it = 0; it < ntiles; ++it) {
-                const int acc = it & 1;
-                mbar_wait_sleep(&tempty_bar[acc], ((tph >> acc) & 1u) ^ 1u);
-                tph ^= 1u << acc;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_tmem = tmem_d + (uint32_t)acc * B2_TN;
+        // The whole warp runs the loop and one ELECTED lane issues: every operand is then warp-uniform for the compiler
+        // (warp index and TMEM base come through a shuffle from lane 0), so each tcgen05.mma is one UIADD3 + UTCIMMA.
+        // Inside an `if (lane == 0)` the same code compiled to a 12-instruction waterfall loop per MMA (R2UR, ELECT,
+        // BRA.U.ANY) whose ~130-cycle latency -- not the 32-cycle MMA -- set the tile time (tensor pipe 26 % active).
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(B2_TN >> 3) << 17) | ((uint32_t)(B2_TM >> 4) << 24);
+        const uint64_t desc0 = bm_desc(smem_addr(Bs), B2_TN * 16u, 128u);
+        for (int it = 0; it < ntiles; ++it) {
+            const int acc = it & 1, bs = it & (B2_SLOTS - 1);
+            mbar_wait_backoff(&tempty_bar[acc], ((uint32_t)(it >> 1) & 1u) ^ 1u, 32);
+            mbar_wait_backoff(&full_bar[bs], (uint32_t)(it / B2_SLOTS) & 1u, 32);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_tmem = tmem_d + (uint32_t)acc * B2_TN;
+            const uint64_t desc_t = desc0 + (uint64_t)((uint32_t)bs * (B2_SLOT_BYTES >> 4));
+            if (bm_elect_one()) {
                 for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait_sleep(&full_bar[stage], phase);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < BM_KB / 32; ++j) {
-                        const uint64_t bdesc = bm_desc(b_base + (uint32_t)stage * B2_TN * BM_KB + (uint32_t)j * 2u * B2_TN * 16u,
-                                                       B2_TN * 16u, 128u);
-                        // A: 8 columns (32 K-elements) per MMA
-                        bm_mma_i8_ts(d_tmem, tmem_a + (uint32_t)(kb * (BM_KB / 4) + 8 * j), bdesc, idesc, (kb | j) != 0 ? 1u : 0u);
-                    }
-                    bm_commit(&empty_bar[stage]);
-                    if (++stage == B2_STAGES) { stage = 0; phase ^= 1u; }
+                    for (int j = 0; j < BM_KB / 32; ++j)      // A: 8 columns (32 K-elements), B: two 16-byte K-chunks per MMA
+                        bm_mma_i8_ts(d_tmem, tmem_a + (uint32_t)(kb * (BM_KB / 4) + 8 * j),
+                                     desc_t + (uint64_t)((kb * B2_TN * BM_KB + j * 2 * B2_TN * 16) >> 4), idesc, (kb | j) != 0 ? 1u : 0u);
                 }
+                bm_commit(&empty_bar[bs]);
                 bm_commit(&tfull_bar[acc]);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
-        // ================= EPILOGUE: thread = landmark (TMEM lane), 32 candidates (columns) of the tile =================
-        const int q = warp & 3, half = (warp - 4) >> 2;
+        // ================= EPILOGUE: thread = landmark (TMEM lane), B2_HN candidates (columns) of the tile =================
+        const int q = warp & 3, cg = (warp - B2_XW) >> 2;
         const int l = l0 + 32 * q + lane;
-        constexpr int HN = B2_TN / 2;
-        const double zn = l < p.L ? __ldg(p.zn + l) : 0.0;
-        double acc[HN];
+        const double zne = (l < p.L ? __ldg(p.zn + l) : 0.0) + 1e-6;
+        double acc[B2_HN];
 #pragma unroll
-        for (int j = 0; j < HN; ++j) acc[j] = 0.0;
-        uint32_t tph = 0;
+        for (int j = 0; j < B2_HN; ++j) acc[j] = 0.0;
         for (int it = 0; it < ntiles; ++it) {
             const int a = it & 1;
-            mbar_wait_sleep(&tfull_bar[a], (tph >> a) & 1u);
-            tph ^= 1u << a;
+            mbar_wait_backoff(&tfull_bar[a], (uint32_t)(it >> 1) & 1u, 256);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t v[32];
-            bm_tmem_ld32(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)a * B2_TN + (uint32_t)half * HN, v);
+            uint32_t v[B2_HN];
+            bm_tmem_ldn(tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)a * B2_TN + (uint32_t)cg * B2_HN, v);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) bm_arrive(&tempty_bar[a]);
-            const double2* m = reinterpret_cast<const double2*>(meta + ((size_t)(it & (B2_META - 1)) * B2_TN + half * HN) * 2);
+            const double2* m = reinterpret_cast<const double2*>(meta + ((size_t)(it & (B2_META - 1)) * B2_TN + cg * B2_HN) * 2);
 #pragma unroll
-            for (int j = 0; j < HN; ++j) {
-                const double2 we = m[j];                  // (w, eps + |x|^2) of candidate j: broadcast load
-                acc[j] = fma(tanimoto_bits_value(__hiloint2double(0x43300000, (int)v[j]) - 4503599627370496.0, we.y, zn),
-                             we.x, acc[j]);
+            for (int j = 0; j < B2_HN; ++j) {
+                const double2 we = m[j];                  // (w, |x|^2) of candidate j: broadcast load
+                const double dot = __hiloint2double(0x43300000, (int)v[j]) - 4503599627370496.0;
+                acc[j] = fma(tanimoto_bits_value(dot, we.y, zne), we.x, acc[j]);
             }
         }
         if (l < p.L) {
 #pragma unroll
-            for (int j = 0; j < HN; ++j) {
-                const int g = g0 + half * HN + j;
+            for (int j = 0; j < B2_HN; ++j) {
+                const int g = g0 + cg * B2_HN + j;
                 if (g < p.S) p.out[((int64_t)blockIdx.z * p.S + g) * p.L + l] = acc[j] * p.scale;
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == BM_MMA_WARP) {
+    if (warp == B2_MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
-size_t bits_mma2_smem() { return (size_t)B2_STAGES * B2_TN * BM_KB + (size_t)B2_META * B2_TN * 2 * 8 + 128; }
+size_t bits_mma2_smem() {
+    return (size_t)B2_SLOTS * B2_SLOT_BYTES + (size_t)B2_META * B2_TN * 2 * 8 +
+           (size_t)B2_RING * BM_MAXW * B2_TN * 8 + 2 * (size_t)B2_RING * B2_TN * 8 + (size_t)B2_IRING * B2_TN * 4 + 128;
+}
 
 size_t bits_mma_smem(int W) {
     const size_t K = (size_t)W * 64;
@@ -531,7 +586,7 @@ int launch_bits_mma2(const BitsMmaParams& p, dim3 grid, cudaStream_t st) {
         SOBER_CUDA_CHECK(cudaFuncSetAttribute(group_bits_mma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) configured[dev] = 1;
     }
-    group_bits_mma2_kernel<<<grid, BM_THREADS, smem, st>>>(p);
+    group_bits_mma2_kernel<<<grid, B2_THREADS, smem, st>>>(p);
     SOBER_LAUNCH_CHECK("group_bits_mma2");
     return SOBER_OK;
 }

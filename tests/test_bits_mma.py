@@ -46,7 +46,8 @@ def test_mma_gram_bitwise_equals_popcount_kernel(ops, cuda_device, d, density):
     assert torch.equal(out[5], out[4])
     kern = ok.Kernel(ok.BareModel(ok.make_kernel("tanimoto", 1.0, 1.7).to(cuda_device)), mode="kernel")
     want = kern(Z, X).T
-    assert float((out[0] - want).abs().max() / want.abs().max()) < 1e-13
+    # one Newton step on the MUFU reciprocal seed: 3e-13 measured (the kernel matrix has to match to 1e-10)
+    assert float((out[0] - want).abs().max() / want.abs().max()) < 1e-12
 
 
 @pytest.mark.parametrize("n_local,S,pos0", [(50_123, 1000, 777), (200_000, 1000, 0), (12_345, 200, 31), (4_100, 64, 0)])

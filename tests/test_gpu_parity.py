@@ -425,7 +425,8 @@ def test_tanimoto_popcount_gram_matches_oracle(ops, cuda_device, d, density):
     center, inv_ls = scaled(spec, Z, cuda_device)
     got = rec._gram_T(rec._points(X, spec, center, inv_ls), rec._table(Z, spec, center, inv_ls)).T
     want = kern(Z, X)
-    assert rel(got, want) < 1e-13
+    # north_star tolerance: 1e-10.  One Newton step on the MUFU reciprocal seed (csrc/common.cuh): 3.3e-13 measured
+    assert rel(got, want) < 1e-12
 
 
 @pytest.mark.parametrize("fam,nu,d", [("rbf", None, 24), ("matern", 2.5, 24), ("matern", 1.5, 100), ("rbf", None, 640)])
