@@ -251,17 +251,17 @@ class Runner:
         """The same metric through the public API with HOST buffers: pinned inputs, host->device copies of the
         candidates and weights and the device->host read of (idx, w) inside the timed region, every step."""
         Xh, muh = self.X.cpu().pin_memory(), self.mu.cpu().pin_memory()
-        wh = torch.empty_like(muh).pin_memory()
-        for _ in range(2):
-            wh.copy_(muh)
-            idx_e, w_e = self.step(wh, Xh)
+        # recombination() turns its init_weights into the sparse solution IN PLACE, so every step gets its own pinned
+        # copy of the input weights, made here, outside the timed region (a host-to-host copy is not part of the path)
+        whs = [muh.clone().pin_memory() for _ in range(steps + 2)]
+        for k in range(2):
+            idx_e, w_e = self.step(whs[steps + k], Xh)
         self.barrier()
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_ev.record()
-        for _ in range(steps):
+        for k in range(steps):
             flush.zero_()
-            wh.copy_(muh)
-            idx_e, w_e = self.step(wh, Xh)
+            idx_e, w_e = self.step(whs[k], Xh)
             idx_host, w_host = idx_e.cpu(), w_e.cpu()
         e_ev.record()
         self.barrier()

@@ -138,12 +138,34 @@ class CudaOps:
         self.launches += 1
         return PointSet(P, ldp, P[:, d], ldp, n, d)
 
-    def make_records(self, X, center, inv_ls, idx=None, mu=None):
+    def upload_chunks(self, host, min_rows=1 << 16, max_chunks=8):
+        """Host (pinned) -> device copy of a row-major float64 matrix in row chunks on a side stream.  Returns the device
+        tensor and [(row_begin, row_end, event)]: a consumer makes its stream wait for a chunk's event before reading the
+        rows, so the first K1 pass starts on chunk 0 while the rest is still crossing PCIe."""
+        n = host.shape[0]
+        out = torch.empty(host.shape, dtype=torch.float64, device=self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream(self.device))
+        out.record_stream(cs)
+        step = max(min_rows, -(-n // max_chunks))
+        chunks = []
+        with torch.cuda.stream(cs):
+            for a in range(0, n, step):
+                b = min(n, a + step)
+                out[a:b].copy_(host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+                chunks.append((a, b, ev))
+        return out, chunks
+
+    def make_records(self, X, center, inv_ls, idx=None, mu=None, out=None):
         """Gather + (x - c) * inv_ls + norm + weight into the record layout (one 16-byte aligned row per point)."""
         d = X.shape[1]
         m = X.shape[0] if idx is None else idx.numel()
         ldr = record_stride(d)
-        rec = torch.empty((m, ldr), dtype=torch.float64, device=self.device)
+        rec = torch.empty((m, ldr), dtype=torch.float64, device=self.device) if out is None else out
         with self._guard():
             t0 = self._begin("make_records")
             check(self.lib.sober_make_records(_ptr(X), X.stride(0), d, _ptr(center), _ptr(inv_ls), _ptr(idx), _ptr(mu),

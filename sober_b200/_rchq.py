@@ -18,6 +18,7 @@ enabled (``sober_b200.distributed``) candidates are row-sharded: each rank owns 
 and the only collective per iteration is one all-reduce of the (S x L') accumulator.
 """
 import itertools
+import threading
 import time
 
 import contextlib
@@ -26,7 +27,7 @@ import torch
 
 from . import _car, _lib, _nystrom, _psd
 from ._kernel_spec import introspect
-from ._ops import LandmarkTable, PointSet
+from ._ops import LandmarkTable, PointSet, record_stride
 from ._settings import options
 
 
@@ -111,9 +112,13 @@ class Alive:
 
     def __init__(self, idx, mass, rec=None):
         self.idx, self.mass, self.rec = idx, mass, rec
+        self.pending = None      # [(begin, end, event)]: record rows still to be built from candidates in flight to the device
 
     def tail(self, t0):
         return Alive(self.idx[t0:], self.mass[t0:], None if self.rec is None else self.rec[t0:])
+
+    def part(self, a, b):
+        return Alive(self.idx[a:b], self.mass[a:b], None if self.rec is None else self.rec[a:b])
 
 
 class _StageClock:
@@ -277,7 +282,17 @@ class Recombiner:
     def run(self, pts_rec, pts_nys, num_pts, kernel, init_weights=None, calc_obj=None):
         ops, comm, o = self.ops, self.comm, self.opts
         dev = ops.device
-        X = ops.f64(pts_rec)
+        # Candidates in pinned host memory (the end-to-end path): the copy runs in row chunks on a side stream and the
+        # first K1 pass consumes the chunks as they land (record layout, plain kernel mode); every other path simply
+        # waits for the whole copy.
+        incoming = None
+        if (torch.is_tensor(pts_rec) and pts_rec.device.type == "cpu" and pts_rec.dtype == torch.float64
+                and pts_rec.dim() == 2 and pts_rec.is_contiguous() and pts_rec.is_pinned() and dev.type == "cuda"
+                and o.overlap and o.stats is None and calc_obj is None and hasattr(ops, "upload_chunks")
+                and pts_rec.shape[0] >= (1 << 18)):
+            X, incoming = ops.upload_chunks(pts_rec)
+        else:
+            X = ops.f64(pts_rec)
         Z = ops.f64(pts_nys)
         if X.dim() != 2 or Z.dim() != 2 or X.shape[1] != Z.shape[1]:
             raise ValueError("pts_rec (N, d) and pts_nys (L, d) must be 2-D with the same d")
@@ -289,10 +304,23 @@ class Recombiner:
 
         if init_weights is None:
             mu = torch.full((n_rows,), 1.0, dtype=torch.float64, device=dev) / n_total
+            clearing = None
         else:
+            clearing = None
             if init_weights.shape != (n_rows,):
                 raise ValueError("init_weights must have shape (len(pts_rec),)")
             mu = ops.f64(init_weights)
+            if init_weights.device.type == "cpu" and dev.type == "cuda" and n_rows >= (1 << 18):
+                # the caller's HOST vector ends up all zero but for <= b entries: clear it beside the GPU work instead
+                # of after it (80 MB of memset at 1e7 candidates), once the upload above has read it
+                uploaded = torch.cuda.Event()
+                uploaded.record(torch.cuda.current_stream(dev))
+
+                def _clear():
+                    uploaded.synchronize()
+                    init_weights.zero_()
+                clearing = threading.Thread(target=_clear, daemon=True)
+                clearing.start()
 
         clock = _StageClock(o.stats, dev)
         spec = introspect(kernel) if o.fuse else None
@@ -333,6 +361,9 @@ class Recombiner:
                         h = torch.arange(d + 1, dtype=torch.float64, device=dev)
                         self._lut = _family_values(spec.family, h * step).contiguous()
         records = self._use_records(spec, d) and not self._bits
+        if incoming is not None and not (records and spec.mode == "kernel" and self.trace is None):
+            torch.cuda.current_stream(dev).wait_event(incoming[-1][2])
+            incoming = None
 
         clock.lap("setup")
         lm = self._landmarks(Z, spec, center, inv_ls)
@@ -346,7 +377,14 @@ class Recombiner:
         # every weight non-zero (the usual case): the alive-list is the identity and the record pass reads X as one
         # contiguous stream instead of gathering rows
         gather = None if n_local == n_rows else idx
-        alive = Alive(idx, mass, ops.make_records(X, center, inv_ls, gather, mass).rec if records else None)
+        if incoming is not None and (gather is not None or n_local <= S):
+            torch.cuda.current_stream(dev).wait_event(incoming[-1][2])
+            incoming = None
+        if incoming is not None:
+            alive = Alive(idx, mass, torch.empty((n_rows, record_stride(d)), dtype=torch.float64, device=dev))
+            alive.pending = incoming
+        else:
+            alive = Alive(idx, mass, ops.make_records(X, center, inv_ls, gather, mass).rec if records else None)
         live = comm.all_gather_ints(n_local, dev)
         pos0, remaining = sum(live[:comm.rank]), sum(live)
         obj = None if calc_obj is None else (-1 * calc_obj(pts_rec.to(dev))).to(torch.float64)
@@ -389,7 +427,19 @@ class Recombiner:
                 if alive.rec is not None:
                     alive.rec[:, d + 1] = wts
                 src = Alive(alive.idx, wts, alive.rec)
-            at, totw = self._accumulate(st, src, n_local, pos0, ES, S)
+            if alive.pending is not None:
+                # pipelined upload: build the records of a chunk and add its group sums as soon as its rows have landed
+                # (a chunk is handled like a rank's shard: positions [pos0 + a, pos0 + b))
+                at = totw = None
+                stream = torch.cuda.current_stream(dev)
+                for a, b, landed in alive.pending:
+                    stream.wait_event(landed)
+                    ops.make_records(X[a:b], center, inv_ls, None, alive.mass[a:b], out=alive.rec[a:b])
+                    at_c, tw_c = self._accumulate(st, alive.part(a, b), b - a, pos0 + a, ES, S)
+                    at, totw = (at_c, tw_c) if at is None else (at.add_(at_c), totw.add_(tw_c))
+                alive.pending = None
+            else:
+                at, totw = self._accumulate(st, src, n_local, pos0, ES, S)
             if m_x is not None:
                 lead = pos0 % S
                 padded = torch.zeros(-(-(lead + t0) // S) * S, dtype=torch.float64, device=dev)
@@ -530,7 +580,10 @@ class Recombiner:
             if mu.data_ptr() == init_weights.data_ptr():
                 ops.scatter_result(mu, loc, w_loc)
             else:
-                init_weights.zero_()
+                if clearing is not None:
+                    clearing.join()
+                else:
+                    init_weights.zero_()
                 init_weights[loc.to(init_weights.device)] = w_loc.to(init_weights.device, init_weights.dtype)
             sel_w = sel_w.to(init_weights.dtype)
         return sel_idx, sel_w

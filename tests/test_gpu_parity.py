@@ -765,3 +765,36 @@ def test_full_size_overlap_and_graphs(ops, cuda_device):
                 torch.manual_seed(5)
                 res[fancy] = sober_b200.recombination(X, Z, 200, kern, None, None)
     assert torch.equal(res[False][0], res[True][0]) and float((res[False][1] - res[True][1]).abs().max()) < 1e-12
+
+
+def test_pipelined_upload_matches_device_resident_input(ops, cuda_device):
+    """Candidates in pinned host memory are copied in row chunks on a side stream while the first K1 pass consumes the
+    chunks that have landed (_rchq.run / _ops.upload_chunks).  Same selection as with the candidates already on the
+    device, weights to rounding (the chunked group sums differ in summation order only), result written back into the
+    caller's host weight vector."""
+    import sober_b200
+    from sober_b200 import _nystrom
+    g = torch.Generator().manual_seed(11)
+    N, d, L, b = 300_000, 6, 300, 40
+    X = torch.rand(N, d, dtype=torch.float64, generator=g)
+    mu = torch.rand(N, dtype=torch.float64, generator=g) + 0.1
+    mu /= mu.sum()
+    Z = X[torch.randperm(N, generator=g)[:L]].clone().to(cuda_device)
+    kern = ok.Kernel(ok.BareModel(ok.make_kernel("matern", [0.7] * d, 1.3).to(cuda_device)), mode="kernel")
+    R = torch.randn(L, b - 1, dtype=torch.float64, generator=g).to(cuda_device)
+    out = {}
+    for where in ("device", "pinned"):
+        Xin = X.to(cuda_device) if where == "device" else X.clone().pin_memory()
+        w_in = mu.clone().to(cuda_device) if where == "device" else mu.clone().pin_memory()
+        _nystrom._injected_test_matrix = R
+        try:
+            with warnings.catch_warnings(), sober_b200.configure(mode="fast"):
+                warnings.simplefilter("ignore")
+                idx, w = sober_b200.recombination(Xin, Z, b, kern, None, None, init_weights=w_in)
+        finally:
+            _nystrom._injected_test_matrix = None
+        out[where] = (idx.cpu(), w.cpu(), w_in.cpu())
+    assert torch.equal(out["device"][0], out["pinned"][0])
+    assert float((out["device"][1] - out["pinned"][1]).abs().max()) < 1e-9
+    assert float((out["device"][2] - out["pinned"][2]).abs().max()) < 1e-9
+    assert abs(float(out["pinned"][2].sum()) - 1.0) < 1e-9
