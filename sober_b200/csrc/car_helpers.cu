@@ -7,17 +7,18 @@ namespace sober {
 
 // scaled[i, 0] = 1 / sqrt(S);  scaled[i, 1 + j] = (F[i, j] / div[i]) / ||column||   -- barycentres (SOBER/_rchq.py:166),
 // the ones column of the design matrix (:229) and the column normalisation of the projector null space in one pass.
-// 32 columns per CTA, 8 row lanes per column.
-__global__ void __launch_bounds__(256) car_prepare_kernel(const double* __restrict__ F, int64_t ldf,
-                                                          const double* __restrict__ div, int S, int n,
-                                                          double* __restrict__ out, int64_t ldo) {
-    __shared__ double part[8][33];
+// 32 columns per CTA, 32 row lanes per column (the FP64 divisions are the cost: 2 S / 32 per thread).
+constexpr int PREP_RL = 32;
+__global__ void __launch_bounds__(32 * PREP_RL) car_prepare_kernel(const double* __restrict__ F, int64_t ldf,
+                                                                   const double* __restrict__ div, int S, int n,
+                                                                   double* __restrict__ out, int64_t ldo) {
+    __shared__ double part[PREP_RL][33];
     __shared__ double inv_norm[32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + tx;          // column of the design matrix, 0 = ones
     double ss = 0.0;
     if (c >= 1 && c <= n) {
-        for (int i = ty; i < S; i += 8) {
+        for (int i = ty; i < S; i += PREP_RL) {
             double v = F[(int64_t)i * ldf + (c - 1)];
             if (div) v /= div[i];
             ss = fma(v, v, ss);
@@ -28,14 +29,14 @@ __global__ void __launch_bounds__(256) car_prepare_kernel(const double* __restri
     if (ty == 0) {
         double s = 0.0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) s += part[q][tx];
+        for (int q = 0; q < PREP_RL; ++q) s += part[q][tx];
         if (c == 0) s = (double)S;
         inv_norm[tx] = 1.0 / fmax(sqrt(s), 1e-300);
     }
     __syncthreads();
     if (c <= n) {
         const double sc = inv_norm[tx];
-        for (int i = ty; i < S; i += 8) {
+        for (int i = ty; i < S; i += PREP_RL) {
             double v = 1.0;
             if (c >= 1) {
                 v = F[(int64_t)i * ldf + (c - 1)];
@@ -126,7 +127,7 @@ using namespace sober;
 extern "C" int sober_car_prepare(const double* F, int64_t ldf, const double* div, int32_t S, int32_t n, double* out,
                                  int64_t ldo, void* stream) {
     if (!F || !out || S <= 0 || n < 0 || ldf < n || ldo < n + 1) return SOBER_ERR_ARG;
-    car_prepare_kernel<<<(unsigned)ceil_div(n + 1, 32), 256, 0, (cudaStream_t)stream>>>(F, ldf, div, S, n, out, ldo);
+    car_prepare_kernel<<<(unsigned)ceil_div(n + 1, 32), 32 * PREP_RL, 0, (cudaStream_t)stream>>>(F, ldf, div, S, n, out, ldo);
     SOBER_LAUNCH_CHECK("car_prepare");
     return SOBER_OK;
 }
