@@ -56,3 +56,22 @@ class Case:
 
 # the fast mode's null-space basis restated with LAPACK (one definition, shared with bench.py's parity block)
 projector_nullspace = oracle_rchq.projector_nullspace
+
+
+def fbgp_case(device="cpu"):
+    """A FullyBayesianGP stand-in (oracle/fbgp.py): 12 exact GPs with different hyperparameters, distilled weights w_qd."""
+    from oracle import fbgp as ofb
+    g = torch.Generator().manual_seed(21)
+    X = torch.rand(1500, 3, dtype=torch.float64, generator=g)
+    Z = X[torch.randperm(1500, generator=g)[:40]].clone()
+    mu = torch.rand(1500, dtype=torch.float64, generator=g)
+    mu /= mu.sum()
+    xo = torch.rand(20, 3, dtype=torch.float64, generator=g)
+    yo = torch.sin(4.0 * xo).sum(-1)
+    X, Z, mu, xo, yo = (t.to(device) for t in (X, Z, mu, xo, yo))
+    models = [ok.GPModel(ok.make_kernel("matern", [ls], os_).to(device), xo, yo, noise=1e-3)
+              for ls, os_ in ((0.3, 1.0), (0.5, 0.7), (0.8, 1.4), (1.2, 1.0), (0.4, 2.0), (0.9, 0.5),
+                              (0.6, 1.1), (1.5, 0.9), (0.35, 1.3), (0.7, 0.8), (1.0, 1.6), (0.45, 0.6))]
+    w_qd = torch.rand(len(models), dtype=torch.float64, generator=g)
+    w_qd /= w_qd.sum()
+    return X, Z, mu, models, w_qd.to(device), ofb

@@ -798,3 +798,30 @@ def test_pipelined_upload_matches_device_resident_input(ops, cuda_device):
     assert float((out["device"][1] - out["pinned"][1]).abs().max()) < 1e-9
     assert float((out["device"][2] - out["pinned"][2]).abs().max()) < 1e-9
     assert abs(float(out["pinned"][2].sum()) - 1.0) < 1e-9
+
+
+def test_fbgp_kernel_through_the_generic_path_on_gpu(ops, cuda_device):
+    """``FullyBayesianGP.marginal_predictive_covariance`` (SOBER/FBGP/_fully_Bayesian_gp.py:354-371, restated in
+    oracle/fbgp.py) is an opaque 2-D-only callable: tiles of it are evaluated on the device and reduced by
+    sober_group_accumulate_gram; same selection as the CPU oracle with the broadcast form of the formula."""
+    import sober_b200
+    from _cases import fbgp_case
+    X, Z, mu, models, w_qd, ofb = fbgp_case()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(7)
+        idx_o, w_o = oracle.recombination(X, Z, 8, ofb.FullyBayesianGP(models, w_qd, strict=False).marginal_predictive_covariance,
+                                          None, None, init_weights=mu.clone())
+    Xg, Zg, mug, models_g, wq_g, _ = fbgp_case(cuda_device)
+    kern = ofb.FullyBayesianGP(models_g, wq_g, strict=True).marginal_predictive_covariance
+    with warnings.catch_warnings(), sober_b200.configure(mode="parity"):
+        warnings.simplefilter("ignore")
+        torch.manual_seed(7)
+        idx, w = sober_b200.recombination(Xg, Zg, 8, kern, None, None, init_weights=mug)
+    assert len(idx) <= 8 and bool((w > 0).all()) and abs(float(w.sum()) - 1.0) < 1e-12
+    # parity mode on another device than the oracle: the range finder's normals differ (CPU vs CUDA generator), so the
+    # comparison is on the invariants and on the quadrature error of the selected batch
+    kern_cpu = ofb.FullyBayesianGP(models, w_qd, strict=False).marginal_predictive_covariance
+    mmd_o = oracle.mmd_squared(kern_cpu, X, mu, idx_o, w_o)
+    mmd_g = oracle.mmd_squared(kern_cpu, X, mu, idx.cpu(), w.cpu())
+    assert float(mmd_g) <= 10 * float(mmd_o) + 1e-12

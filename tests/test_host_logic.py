@@ -10,7 +10,7 @@ from oracle import rchq as oracle
 from sober_b200 import Recombiner, configure
 from sober_b200._rchq import KeepMap
 from sober_b200 import _nystrom
-from _cases import LOOP_CASES, CASES, Case, projector_nullspace
+from _cases import LOOP_CASES, CASES, Case, fbgp_case, projector_nullspace
 from _cpu_ops import TorchOps
 
 # rbf2d_branin is the chaotic regime (rank-deficient Gram, SURVEY.md TL;DR 6): a 1e-16 change in the group sums
@@ -176,3 +176,32 @@ def test_keepmap_counts_match_mask_bookkeeping():
         alive = [p for p in range(R) if (p < ES and kept[p % S]) or (p >= ES and kept[S - 1])]
         for p in range(R + 1):
             assert km.before(p) == sum(1 for q in alive if q < p)
+
+
+def test_fbgp_kernel_reference_loop_branch_raises_generic_path_works():
+    """SOBER/_sober.py:63-65 hands ``FullyBayesianGP.marginal_predictive_covariance`` (SOBER/FBGP/_fully_Bayesian_gp.py:
+    354-371) to recombination.  As written it only takes 2-D inputs, so the reference's loop branch (3-D candidates,
+    SOBER/_rchq.py:124) raises; the product's generic path calls it on 2-D tiles and selects the same points as the
+    oracle run with the broadcast-capable form of the same formula."""
+    X, Z, mu, models, w_qd, ofb = fbgp_case()
+    b = 8
+    strict = ofb.FullyBayesianGP(models, w_qd, strict=True)
+    with pytest.raises(RuntimeError), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(7)
+        oracle.recombination(X, Z, b, strict.marginal_predictive_covariance, None, None, init_weights=mu.clone())
+    loose = ofb.FullyBayesianGP(models, w_qd, strict=False)
+    assert torch.equal(strict.marginal_predictive_covariance(Z, X[:50]), loose.marginal_predictive_covariance(Z, X[:50]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(7)
+        idx_o, w_o = oracle.recombination(X, Z, b, loose.marginal_predictive_covariance, None, None,
+                                          init_weights=mu.clone())
+    with warnings.catch_warnings(), configure(mode="parity", generic_chunk=333) as opts:
+        warnings.simplefilter("ignore")
+        torch.manual_seed(7)
+        m = mu.clone()
+        idx, w = Recombiner(TorchOps(), opts=opts).run(X, Z, b, strict.marginal_predictive_covariance, init_weights=m)
+    assert torch.equal(idx, idx_o)
+    assert float((w - w_o).abs().max()) < 1e-8
+    assert abs(float(w.sum()) - 1.0) < 1e-12 and int((m != 0).sum()) == len(idx)
