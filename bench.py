@@ -499,8 +499,8 @@ def main():
     if not args.no_extras and args.workload == "auto" and args.mode == "fast":
         if world > 1:
             wk = Runner("c2", dev, rank, world)
-            ms, _, _ = wk.timed(max(3, args.steps // 2), 2, flush)
-            ksteps = max(3, args.steps // 2)
+            ksteps = max(5, args.steps)
+            ms, _, _ = wk.timed(ksteps, 3, flush)
             extras["weak_c2"] = {"workload": WORKLOADS["c2"][6], "scaling": "weak", "n_rec_total": wk.n_total,
                                  "value": wk.n_total * ksteps / (ms * 1e-3), "unit": "candidates/s",
                                  "ms_per_step": ms / ksteps, "steps": ksteps}
