@@ -290,6 +290,10 @@ class Runner:
         e_ev.record()
         self.barrier()
         ms = self.max_over_ranks(s_ev.elapsed_time(e_ev))
+        # the host-buffer path returns the same kind of answer: at most b points, weights summing to the input mass, and
+        # the caller's host weight vector turned into that sparse solution in place (this rank's part of it)
+        assert len(idx_host) <= self.b and abs(float(w_host.sum()) - 1.0) < 1e-9, "e2e result failed its invariants"
+        assert int((whs[steps - 1] != 0).sum()) <= self.b, "e2e: init_weights was not turned into the sparse solution"
         return ms, Xh.numel() * 8 + muh.numel() * 8, idx_host.numel() * 8 + w_host.numel() * 8
 
 
