@@ -419,20 +419,33 @@ __global__ void __launch_bounds__(CP_THREADS, 1) car_panel_kernel(const CarPanel
                 if (q < bw && okk && row0 + ri == jblk_s[q]) dd = true;
             }
             if (okk) {
-                for (int c = ci; c < glen; c += tc) {
-                    double rr[B];
-                    const double2* gp = reinterpret_cast<const double2*>(gbuf + (size_t)c * B);
+                // CU_IL columns in flight per thread: their loads are issued together and the CU_IL chains of 8 dependent
+                // FMAs interleave (one column at a time left the FP64 pipe waiting on a single chain)
+                constexpr int CU_IL = 4;
+                for (int c0 = ci; c0 < glen; c0 += CU_IL * tc) {
+                    double rr[CU_IL][B], acc[CU_IL];
 #pragma unroll
-                    for (int q = 0; q < B; q += 2) {
-                        const double2 v2 = gp[q / 2];
-                        rr[q] = v2.x;
-                        rr[q + 1] = v2.y;
+                    for (int u = 0; u < CU_IL; ++u) {
+                        const bool live = c0 + u * tc < glen;
+                        const int c = live ? c0 + u * tc : glen - 1;       // R of a clamped column is loaded, never used
+                        const double2* gp = reinterpret_cast<const double2*>(gbuf + (size_t)c * B);
+#pragma unroll
+                        for (int q = 0; q < B; q += 2) {
+                            const double2 v2 = gp[q / 2];
+                            rr[u][q] = v2.x;
+                            rr[u][q + 1] = v2.y;
+                        }
+                        acc[u] = live ? panel[(size_t)(b0 + bw + c) * rpcp + ri] : 0.0;
                     }
-                    double* x = panel + (size_t)(b0 + bw + c) * rpcp + ri;
-                    double acc = *x;
 #pragma unroll
-                    for (int q = 0; q < B; ++q) acc = fma(-uu[q], rr[q], acc);
-                    *x = dd ? 0.0 : acc;
+                    for (int q = 0; q < B; ++q)
+#pragma unroll
+                        for (int u = 0; u < CU_IL; ++u) acc[u] = fma(-uu[q], rr[u][q], acc[u]);
+#pragma unroll
+                    for (int u = 0; u < CU_IL; ++u) {
+                        const int c = c0 + u * tc;
+                        if (c < glen) panel[(size_t)(b0 + bw + c) * rpcp + ri] = dd ? 0.0 : acc[u];
+                    }
                 }
             }
             __syncthreads();                       // (C) the rest of the panel is up to date
