@@ -132,23 +132,72 @@ def _step_constants(S, dim, device):
     return c
 
 
-def _reduce_step_fused(ops, feats, mass, divide):
+def projector_rows_sharded(comm, scaled):
+    """The projector null space of ``_reduce_step_fused`` with its S-dimension work split over the ranks of ``comm``.
+
+    Every rank holds the same column-scaled design ``scaled`` (S x dim) -- the Caratheodory step is replicated, its
+    inputs are bit-identical after the all-reduce of the group sums -- and at C5 sizes (S = 2002, dim = 1001) the null
+    space is 1.6 ms of GEMMs and a triangular solve per call that eight GPUs would each repeat.  Here rank r takes a
+    contiguous block of rows of ``scaled``: its part of the Gram matrix (all-reduce), its rows of Q = scaled R^-1
+    (all-gather), its part of Q^T Q (all-reduce), and a block of the k = S - dim null-space rows (all-gather).  The
+    Cholesky factorisation and the dim x dim Neumann term stay replicated.  Collectives hand every rank the same bits, so
+    the replicated elimination that follows still takes the same pivots on every rank.
+    Returns (rows (k x S), delta (dim x dim)) like the replicated code path (same formulas; sums in a different order)."""
+    from ._linalg import cholesky_upper, solve_right_upper
+    S, dim = scaled.shape
+    k = S - dim
+    W, r = comm.world, comm.rank
+    dev, f64 = scaled.device, torch.float64
+    step = -(-S // W)
+    lo, hi = min(S, r * step), min(S, (r + 1) * step)
+    part = scaled[lo:hi]
+    gram = part.mH @ part
+    comm.all_reduce(gram)
+    rr, _ = cholesky_upper(gram)
+    q_loc = torch.zeros((step, dim), dtype=f64, device=dev)
+    if hi > lo:
+        q_loc[:hi - lo] = solve_right_upper(rr, part)
+    q_all = torch.empty((W * step, dim), dtype=f64, device=dev)
+    comm.all_gather(q_all, q_loc)
+    qt = q_all[:S]
+    delta = q_loc.mH @ q_loc                              # the padding rows are zero
+    comm.all_reduce(delta)
+    delta.diagonal().sub_(1.0)                            # Q^T Q - I
+    eye = torch.eye(dim, dtype=f64, device=dev)
+    inv = torch.addmm(eye - delta, delta, delta)          # I - Delta + Delta^2
+    kstep = -(-k // W)
+    klo, khi = min(k, r * kstep), min(k, (r + 1) * kstep)
+    mine = torch.zeros((kstep, S), dtype=f64, device=dev)
+    if khi > klo:
+        blk = mine[:khi - klo]
+        blk[:, dim + klo:dim + khi] = torch.eye(khi - klo, dtype=f64, device=dev)
+        blk.addmm_(qt[dim + klo:dim + khi] @ inv, qt.mH, alpha=-1.0)
+    rows_all = torch.empty((W * kstep, S), dtype=f64, device=dev)
+    comm.all_gather(rows_all, mine)
+    return rows_all[:k], delta
+
+
+def _reduce_step_fused(ops, feats, mass, divide, comm=None):
     """The fast-mode step with its bookkeeping folded into two hand-written kernels and the GEMM epilogues:
     ``car_prepare`` (barycentres + ones column + column scaling), Gram / Cholesky / triangular solve, the Neumann-
     corrected projector as three addmm calls (the -I, +I and [0 | I] terms ride on the GEMMs' beta operand), the
     panelled elimination, ``car_summary`` (accuracy check of the projector, survivor counts and ranks).
-    14 launches instead of ~35; same arithmetic as ``projector_rows`` + ``_reduce_step``."""
+    14 launches instead of ~35; same arithmetic as ``projector_rows`` + ``_reduce_step``.
+    With ``comm``: the null space is computed by ``projector_rows_sharded`` (multi-GPU, large S)."""
     from ._linalg import cholesky_upper, solve_right_upper
     from ._settings import options
     S, n = feats.shape
     dim = n + 1
-    neg_eye, eye, e2t = _step_constants(S, dim, feats.device)
     scaled = ops.car_prepare(feats, mass if divide else None)           # (S x dim), unit columns
-    r, _ = cholesky_upper(scaled.mH @ scaled)
-    qt = solve_right_upper(r, scaled)
-    delta = torch.addmm(neg_eye, qt.mH, qt)                             # Q^T Q - I
-    inv = torch.addmm(eye - delta, delta, delta)                        # I - Delta + Delta^2
-    rows = torch.addmm(e2t, qt[dim:, :] @ inv, qt.mH, alpha=-1.0)       # trailing k columns of I - Q (I + Delta)^-1 Q^T
+    if comm is not None:
+        rows, delta = projector_rows_sharded(comm, scaled)
+    else:
+        neg_eye, eye, e2t = _step_constants(S, dim, feats.device)
+        r, _ = cholesky_upper(scaled.mH @ scaled)
+        qt = solve_right_upper(r, scaled)
+        delta = torch.addmm(neg_eye, qt.mH, qt)                             # Q^T Q - I
+        inv = torch.addmm(eye - delta, delta, delta)                        # I - Delta + Delta^2
+        rows = torch.addmm(e2t, qt[dim:, :] @ inv, qt.mH, alpha=-1.0)       # trailing k columns of I - Q (I + Delta)^-1 Q^T
     out = mass.clone()
     ops.car_panel(rows, out, nb_hint=options.car_panel_nb)
     summary, rank = ops.car_summary(out, delta)
@@ -200,12 +249,22 @@ class _ReduceGraph:
         return self.out
 
 
-def reduce_step(ops, feats, mass, use_graph=True, divide=False):
+def reduce_step(ops, feats, mass, use_graph=True, divide=False, comm=None):
     """``_reduce_step``, replayed from a CUDA graph from the second call with the same shapes on (the outputs are then
-    static buffers, valid until the next call).  Falls back to eager execution for good if the capture fails."""
+    static buffers, valid until the next call).  Falls back to eager execution for good if the capture fails.
+    ``comm`` (a multi-rank communicator) with S >= options.car_shard_min: the step runs eagerly with the projector null
+    space split over the ranks (``projector_rows_sharded``; collectives are kept out of graph capture)."""
     fits = getattr(ops, "car_cols_fits", None)
     S, n = feats.shape
     pfits = getattr(ops, "car_panel_fits", None)
+    from ._settings import options
+    if (comm is not None and getattr(comm, "world", 1) > 1 and feats.is_cuda and S >= options.car_shard_min
+            and hasattr(ops, "car_prepare") and options.car_kernel != "legacy" and pfits is not None and S > n + 1
+            and S <= 4096 and pfits(S, S - n - 1)):
+        t0 = ops._begin("car_step_graph")                # same stage label as the graph replays (bench.py's stage table)
+        out = _reduce_step_fused(ops, feats, mass, divide, comm)
+        ops._end("car_step_graph", t0, S - n - 1)
+        return out
     if (not use_graph or not feats.is_cuda or fits is None or S <= n + 1
             or not (fits(S, S - n - 1) or (pfits is not None and pfits(S, S - n - 1)))):
         return _reduce_step(ops, feats, mass, divide)

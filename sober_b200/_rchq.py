@@ -43,6 +43,10 @@ class SingleProcess:
     def all_gather_ints(self, value, device):
         return [int(value)]
 
+    def all_gather(self, out, part):
+        out.copy_(part.reshape(out.shape))
+        return out
+
 
 class Sharded:
     """Row-sharded candidates over a torch.distributed group (NCCL on the GPU box, gloo in the CPU tests)."""
@@ -61,6 +65,11 @@ class Sharded:
         out = torch.empty(self.world, dtype=torch.int64, device=device)
         self.dist.all_gather_into_tensor(out, mine, group=self.group)
         return [int(v) for v in out.tolist()]
+
+    def all_gather(self, out, part):
+        """out (world * m, ...) <- the ranks' equally shaped parts (m, ...), in rank order."""
+        self.dist.all_gather_into_tensor(out, part.contiguous(), group=self.group)
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -538,7 +547,7 @@ class Recombiner:
             if graph_step:
                 # the whole step (barycentres, null space, elimination, survivor counts and ranks) as one CUDA-graph replay
                 wfull, kept, summary, rank = _car.reduce_step(ops, bary, totw, use_graph=o.graphs and o.stats is None,
-                                                              divide=True)
+                                                              divide=True, comm=comm)
                 summary = summary.tolist()                                               # the one host sync of the iteration
                 keep = KeepMap.from_summary(summary, S, ES)
                 retry = _car.needs_retry("projector", keep.K, n_design, bool(summary[S]))
@@ -637,7 +646,8 @@ class Recombiner:
             feats = torch.cat([feats, alive_obj.unsqueeze(1)], 1)
         if self.nullspace is None and o.nullspace == "projector":
             wfull, _, summary, _ = _car.reduce_step(ops, feats, all_mass,
-                                                    use_graph=o.graphs and o.stats is None and self.trace is None)
+                                                    use_graph=o.graphs and o.stats is None and self.trace is None,
+                                                    comm=comm)
             summary = summary.tolist()
             if _car.needs_retry("projector", summary[-2], feats.shape[1] + 1, bool(summary[-1])):
                 wfull = _car.caratheodory(ops, feats, all_mass, "qr")

@@ -53,6 +53,12 @@ class Options:
         self.car_kernel = os.environ.get("SOBER_B200_CAR", "panel")   # "panel": blocked row-distributed cluster kernel
                                       # (csrc/car_panel.cu) for the fused-arithmetic elimination; "legacy": round-1 kernels
         self.car_panel_nb = int(os.environ.get("SOBER_B200_CAR_NB", "0"))   # 0 = automatic panel width
+        # multi-GPU: from this many groups S on, the projector null space of the replicated Caratheodory step is split
+        # over the ranks (_car.projector_rows_sharded, 4 collectives per call).  OFF by default: measured at C5
+        # (S = 2002) on 2 and 8 GPUs the step takes the same 1.6 ms either way -- it is bound by the latency of the
+        # Cholesky factorisation and of the triangular solve, which do not shrink with the row split, and the GEMMs
+        # that do shrink pay for the collectives.  Kept (and tested over gloo and NCCL) for larger S.
+        self.car_shard_min = int(os.environ.get("SOBER_B200_CAR_SHARD_MIN", str(1 << 30)))
         self.stats = None             # optional dict that receives per-stage timings (forces syncs)
 
     def set_mode(self, mode):

@@ -96,3 +96,48 @@ def test_two_rank_kmeans_equals_single_process(split):
     assert torch.equal(c0, c1)
     assert float((c0 - c).abs().max()) < 1e-12
     assert torch.equal(torch.cat([cl0, cl1]), cl)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _projector_worker(rank, world, port, S, dim, out):
+    from sober_b200 import Sharded, _car
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(1)
+        g = torch.Generator().manual_seed(S + dim)
+        a = torch.randn(S, dim, dtype=torch.float64, generator=g)
+        a[:, 0] = 1.0
+        scaled = a / a.norm(dim=0, keepdim=True)
+        rows, delta = _car.projector_rows_sharded(Sharded(), scaled)
+        out[rank] = (rows.clone(), delta.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("S,dim,world", [(90, 31, 2), (64, 33, 3), (50, 49, 2)])
+def test_sharded_projector_null_space(S, dim, world):
+    """``_car.projector_rows_sharded`` (the multi-GPU split of the replicated Caratheodory step's null space): every
+    rank ends with the SAME bits, the rows span the null space of the design, and they equal the single-rank formulas."""
+    from sober_b200 import _car
+    from sober_b200._rchq import SingleProcess
+    port = 29500 + (os.getpid() + 7 * S + dim) % 2000
+    manager = mp.Manager()
+    out = manager.dict()
+    mp.spawn(_projector_worker, args=(world, port, S, dim, out), nprocs=world, join=True)
+    g = torch.Generator().manual_seed(S + dim)
+    a = torch.randn(S, dim, dtype=torch.float64, generator=g)
+    a[:, 0] = 1.0
+    scaled = a / a.norm(dim=0, keepdim=True)
+    rows1, delta1 = _car.projector_rows_sharded(SingleProcess(), scaled)
+    for r in range(1, world):
+        assert torch.equal(out[0][0], out[r][0]) and torch.equal(out[0][1], out[r][1])
+    rows, delta = out[0]
+    assert rows.shape == (S - dim, S)
+    assert float((rows - rows1).abs().max()) < 1e-12 and float((delta - delta1).abs().max()) < 1e-12
+    assert float((rows @ scaled).abs().max()) < 1e-12                   # null space of the design
+    # the trailing columns of the orthogonal projector I - Q Q^T
+    q, _ = torch.linalg.qr(scaled)
+    want = (torch.eye(S, dtype=torch.float64) - q @ q.T)[dim:, :]
+    assert float((rows - want).abs().max()) < 1e-11
