@@ -31,6 +31,8 @@ void set_cuda_error(cudaError_t e, const char* where);
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int sm_count();
+int stream_sm_count(void* stream);   // csrc/partition.cu: the SM-partitioned stream sees fewer SMs
+int partition_sm_count();             // 0 = no partition on this device
 
 // ---------------------------------------------------------------------------------------------------
 // FP64 math tuned for the FP64 pipe (B200: 64 DFMA/clk/SM, no FP64 SFU).  The library exp()/sqrt()/division

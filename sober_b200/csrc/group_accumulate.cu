@@ -616,7 +616,8 @@ struct Plan {
     int64_t rows_per_split, row_begin, row_end;
 };
 
-static bool plan_group(const sober_group_args* a, Plan* pl) {
+static bool plan_group(const sober_group_args* a, Plan* pl, int sms = 0) {
+    if (sms <= 0) sms = sm_count();
     if (!a || a->S <= 0 || a->L <= 0 || a->d <= 0 || a->n_local < 0 || a->pos0 < 0) return false;
     const int64_t hi = a->pos0 + a->n_local;
     pl->row_begin = a->pos0 / a->S;
@@ -642,35 +643,55 @@ static bool plan_group(const sober_group_args* a, Plan* pl) {
         gx = ceil_div(a->S, pl->bits_mma_v1 ? 128 : 64);
         gy = ceil_div(a->L, pl->bits_mma_v1 ? 64 : 128);
         pl->block = dim3(416);
-        target = (int64_t)sm_count() * 3;    // one 167 KB CTA per SM, a few waves
+        target = (int64_t)sms * 3;    // one 167 KB CTA per SM, a few waves
     } else if (pl->bits) {
         gx = ceil_div(a->S, BITS_TG);
         gy = ceil_div(a->L, 8 * 32 * bits_tl((int)a->ldx));
         pl->block = dim3(256);
-        target = (int64_t)sm_count() * 12;
+        target = (int64_t)sms * 12;
     } else if (pl->records) {
         gx = ceil_div(a->S, REC_TG);
         gy = ceil_div(a->L, REC_WARPS * 32 * REC_TL);
         pl->block = dim3(REC_THREADS);
-        target = (int64_t)sm_count() * 12;   // many more CTAs than SMs: the tail wave costs < 1/12
+        target = (int64_t)sms * 12;   // many more CTAs than SMs: the tail wave costs < 1/12
     } else {
         gx = ceil_div(a->S, TN);
         gy = ceil_div(a->L, TM);
         pl->block = dim3(256);
-        target = (int64_t)sm_count() * 8;
+        target = (int64_t)sms * 8;
     }
     int64_t ns = ceil_div(target, gx * gy);
     if (pl->bits_mma) {
         // one CTA per SM: pick the split count whose last wave is fullest (3.46 waves would run as 4: -14 %)
-        const int64_t sms = sm_count();
+        const int64_t smsl = sms;
         int64_t best = ns;
         double best_eff = 0.0;
         for (int64_t c = ns; c <= ns + 6 && c <= rows; ++c) {
             const int64_t ctas = gx * gy * c;
-            const double eff = (double)ctas / (double)(ceil_div(ctas, sms) * sms);
+            const double eff = (double)ctas / (double)(ceil_div(ctas, smsl) * smsl);
             if (eff > best_eff + 1e-9) { best_eff = eff; best = c; }
         }
         ns = best;
+    }
+    if (pl->records && !pl->bits_mma && rows > 0) {
+        // Wave-aware split count for the register kernel (2 CTAs of 256 threads x 126 registers per SM): the CTAs of one
+        // launch do equal work, so the launch takes ceil(CTAs / resident) "waves" of rows_per_split rows each -- 1800
+        // CTAs on 296 slots ran as 7 waves with the last one 8 % full.  Pick the split count that minimises
+        // waves x rows_per_split, plus a quarter of a row per split for the second-stage reduction it feeds.
+        static const int wave_aware = [] { const char* e = getenv("SOBER_B200_K1_WAVES"); return e ? atoi(e) : 1; }();
+        const int64_t resident = (int64_t)sms * 2;
+        if (wave_aware) {
+            int64_t best = ns;
+            double best_cost = 1e300;
+            for (int64_t c = (ns + 1) / 2; c <= ns + 8 && c <= rows; ++c) {
+                if (c < 1) continue;
+                const int64_t rps = ceil_div(rows, c), nsp = ceil_div(rows, rps);
+                const double cost = (double)ceil_div(gx * gy * nsp, resident) * (double)rps + 0.25 * (double)nsp;
+                if (cost < best_cost - 1e-9) { best_cost = cost; best = c; }
+            }
+            ns = best;
+        }
+        if (const char* e = getenv("SOBER_B200_K1_NS")) { if (atoi(e) > 0) ns = atoi(e); }   // tuning aid
     }
     if (ns > rows) ns = rows;
     if (ns < 1) ns = 1;
@@ -732,21 +753,30 @@ static bool launch_family(const Plan& pl, const GroupParams& p, cudaStream_t st)
 
 using namespace sober;
 
+static int64_t plan_workspace(const sober_group_args* a, const Plan& pl) {
+    if (pl.nsplit <= 1) return 0;  // single split: the kernel writes At / totw directly
+    return (int64_t)pl.nsplit * ((int64_t)a->S * a->L + a->S) * 8;
+}
+
+// The split count depends on the SMs the launching stream can use (whole device, or the SM partition of
+// sober_partition_stream): the query does not know the stream and returns the larger of the two needs.
 extern "C" int64_t sober_group_accumulate_workspace(const sober_group_args* a) {
     Plan pl;
     if (!plan_group(a, &pl)) return -1;
-    if (pl.nsplit <= 1) return 0;  // single split: the kernel writes At / totw directly
-    return (int64_t)pl.nsplit * ((int64_t)a->S * a->L + a->S) * 8;
+    int64_t need = plan_workspace(a, pl);
+    const int part = partition_sm_count();
+    if (part > 0 && plan_group(a, &pl, part)) need = std::max(need, plan_workspace(a, pl));
+    return need;
 }
 
 extern "C" int sober_group_accumulate(const sober_group_args* a, void* workspace, int64_t workspace_bytes,
                                       void* stream) {
     Plan pl;
-    if (!plan_group(a, &pl)) return SOBER_ERR_ARG;
+    if (!plan_group(a, &pl, stream_sm_count(stream))) return SOBER_ERR_ARG;
     if (!a->Zt || !a->zn || !a->At || !a->totw) return SOBER_ERR_ARG;
     if (!pl.records && (!a->X || !a->xn)) return SOBER_ERR_ARG;
     if (a->family < SOBER_RBF || a->family > SOBER_HAMMING_LUT) return SOBER_ERR_UNSUPPORTED;
-    const int64_t need = sober_group_accumulate_workspace(a);
+    const int64_t need = plan_workspace(a, pl);
     if (need > workspace_bytes || (need > 0 && !workspace)) return SOBER_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t SL = (int64_t)a->S * a->L;

@@ -36,6 +36,22 @@ Partition g_part[64];
 
 }  // namespace
 
+namespace sober {
+// SMs a launch on ``stream`` can use: the partition's share when it is this device's SM-partitioned stream, else all.
+// K1 sizes its grid in whole waves of resident CTAs, and the first (largest) pass runs on the partition.
+int stream_sm_count(void* stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return sm_count();
+    const Partition& part = g_part[dev];
+    return (stream && part.stream && (void*)part.stream == stream && part.sms > 0) ? part.sms : sm_count();
+}
+int partition_sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    return g_part[dev].stream ? g_part[dev].sms : 0;
+}
+}  // namespace sober
+
 // Stream confined to (all SMs - reserve_sms) of the current device, created on first use and cached per device.
 // *stream = NULL (and SOBER_OK) when the driver cannot partition the device: the caller then simply does not overlap.
 extern "C" int sober_partition_stream(int32_t reserve_sms, void** stream, int32_t* sm_count_out) {

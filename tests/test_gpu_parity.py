@@ -764,7 +764,9 @@ def test_full_size_overlap_and_graphs(ops, cuda_device):
             for _ in range(2):
                 torch.manual_seed(5)
                 res[fancy] = sober_b200.recombination(X, Z, 200, kern, None, None)
-    assert torch.equal(res[False][0], res[True][0]) and float((res[False][1] - res[True][1]).abs().max()) < 1e-12
+    # same points; the weights agree to summation-order rounding (the first K1 pass on the SM-partitioned stream picks its
+    # row-split count for the partition's SM count, so its partial sums are grouped differently)
+    assert torch.equal(res[False][0], res[True][0]) and float((res[False][1] - res[True][1]).abs().max()) < 1e-10
 
 
 def test_pipelined_upload_matches_device_resident_input(ops, cuda_device):
