@@ -677,16 +677,17 @@ static bool plan_group(const sober_group_args* a, Plan* pl, int sms = 0) {
         // Wave-aware split count for the register kernel (2 CTAs of 256 threads x 126 registers per SM): the CTAs of one
         // launch do equal work, so the launch takes ceil(CTAs / resident) "waves" of rows_per_split rows each -- 1800
         // CTAs on 296 slots ran as 7 waves with the last one 8 % full.  Pick the split count that minimises
-        // waves x rows_per_split, plus a quarter of a row per split for the second-stage reduction it feeds.
+        // waves x (rows_per_split + 1/2) -- half a row for a CTA's prologue: exponential table, landmark registers --
+        // plus a quarter of a row per split for the second-stage reduction it feeds.  Small launches (a few dozen rows)
+        // then run as ONE wave of several rows per CTA instead of five waves of single-row CTAs.
         static const int wave_aware = [] { const char* e = getenv("SOBER_B200_K1_WAVES"); return e ? atoi(e) : 1; }();
         const int64_t resident = (int64_t)sms * 2;
         if (wave_aware) {
             int64_t best = ns;
             double best_cost = 1e300;
-            for (int64_t c = (ns + 1) / 2; c <= ns + 8 && c <= rows; ++c) {
-                if (c < 1) continue;
+            for (int64_t c = 1; c <= ns + 8 && c <= rows; ++c) {
                 const int64_t rps = ceil_div(rows, c), nsp = ceil_div(rows, rps);
-                const double cost = (double)ceil_div(gx * gy * nsp, resident) * (double)rps + 0.25 * (double)nsp;
+                const double cost = (double)ceil_div(gx * gy * nsp, resident) * ((double)rps + 0.5) + 0.25 * (double)nsp;
                 if (cost < best_cost - 1e-9) { best_cost = cost; best = c; }
             }
             ns = best;

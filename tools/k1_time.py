@@ -8,7 +8,7 @@ dev = ops.device
 name = os.path.basename(os.environ.get("SOBER_B200_LIB", "default"))
 out = []
 ref = {}
-for (N, L, S) in [(1_000_000, 1000, 400), (250_000, 1000, 400), (60_000, 1000, 400), (2_000_000, 2000, 2000)]:
+for (N, L, S) in [(1_000_000, 1000, 400), (250_000, 1000, 400), (60_000, 1000, 400), (15_000, 1000, 400), (4_000, 1000, 400), (2_000_000, 2000, 2000), (40_000, 2000, 2000)]:
     g = torch.Generator(device=dev).manual_seed(0)
     X = torch.rand(N, 6, dtype=torch.float64, device=dev, generator=g)
     mu = torch.rand(N, dtype=torch.float64, device=dev, generator=g); mu /= mu.sum()
