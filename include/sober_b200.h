@@ -221,6 +221,12 @@ int sober_car_panel(double* basis, int32_t k, int32_t S, double* mu, int32_t nb_
 int sober_car_panel_profiled(double* basis, int32_t k, int32_t S, double* mu, int32_t nb_hint, int32_t* info,
                              void* workspace, int64_t workspace_bytes, int64_t* prof, void* stream);
 
+/* The second count of the remainder (SOBER/_rchq.py:153-164: the points beyond E*S are ALSO added to the last group)
+ * applied to the group sums of one iteration in one launch:  at_last_row (= At + (S-1)*L', L' entries) += tail_at;
+ * totw_out[g] = totw_in[g] (+ tail_tw[0] for g = S-1).  tail_at = tail_tw = NULL: no remainder, totw is just copied. */
+int sober_apply_tail(double* at_last_row, const double* tail_at, int32_t Lp, const double* totw_in,
+                     const double* tail_tw, int32_t S, double* totw_out, void* stream);
+
 /* Fused helpers of one Caratheodory step (csrc/car_helpers.cu), each replacing several library launches:
  *  sober_car_prepare: out (S x (n+1), ldo) = column-normalised design matrix [1 | F / div] -- barycentres
  *    (SOBER/_rchq.py:166; div may be NULL), ones column (:229) and the column scaling of the projector null space.

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "sober_car_panel_profiled": (C.c_int, [_P, _I32, _I32, _P, _I32, _P, _P, _I64, _P, _P]),
     "sober_car_prepare": (C.c_int, [_P, _I64, _P, _I32, _I32, _P, _I64, _P]),
     "sober_car_summary": (C.c_int, [_P, _I32, _P, _I64, _D, _P, _P, _P]),
+    "sober_apply_tail": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P]),
     "sober_update_compact": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _I32, _I32, _I64, _P, _P,
                                        _P, _P, _I64, _I32, _P]),
     "sober_scatter_result": (C.c_int, [_P, _I64, _P, _P, _I64, _P]),

@@ -392,6 +392,17 @@ class CudaOps:
         self.launches += 1
         return summary, rank
 
+    def apply_tail(self, at, totw, tail_at=None, tail_tw=None):
+        """at[S-1] += tail_at (in place) and a copy of ``totw`` with tail_tw added to its last entry: the second count of
+        the remainder (SOBER/_rchq.py:153-164) in one launch.  Without a remainder: just the copy."""
+        S, Lp = at.shape
+        out = torch.empty_like(totw)
+        with self._guard():
+            check(self.lib.sober_apply_tail(_ptr(at[S - 1]), _ptr(tail_at), Lp, _ptr(totw), _ptr(tail_tw), S, _ptr(out),
+                                            self._stream()), "apply_tail")
+        self.launches += 1
+        return out
+
     # -- update + compaction ----------------------------------------------------------------------------------
     def update_compact(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, n_out,
                        rec=None, d=0):

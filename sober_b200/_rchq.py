@@ -425,6 +425,9 @@ class Recombiner:
                 st["post"] = (kx_all, lm["k_zo_w"].contiguous())
         self._m_x = m_x
 
+        fast_tail = (comm.world == 1 and obj is None and m_x is None and not o.fused_projection
+                     and hasattr(ops, "apply_tail") and dev.type == "cuda")
+
         def k1_pass(alive, n_local, pos0, remaining):
             """Grouped kernel-column sums of one iteration: At, totw and the second count of the remainder."""
             ES = (remaining // S) * S
@@ -455,6 +458,14 @@ class Recombiner:
                 padded[lead:lead + t0] = alive.mass[:t0]
                 totw = padded.reshape(-1, S).sum(0)
             Lp = at.shape[1]
+            if fast_tail:
+                # single process, no objective: the second count is applied by ONE kernel (ops.apply_tail) instead of
+                # being packed into ``extra`` for the all-reduce and added with five small torch launches
+                tail = None
+                if t0 < n_local:
+                    tail_at, tail_tw = self._accumulate(st, src.tail(t0), n_local - t0, 0, n_local - t0, 1)
+                    tail = (tail_at[0], tail_tw)
+                return at, totw, tail, t0
             extra = torch.zeros(Lp + 3, dtype=torch.float64, device=dev)
             if t0 < n_local:
                 # second count of the remainder into the last group (SOBER/_rchq.py:153-164)
@@ -474,7 +485,11 @@ class Recombiner:
             if part is not None:
                 def launch_first():
                     first["k1"] = k1_pass(alive, n_local, pos0, remaining)
-                    return first["k1"][:3]
+                    at_, totw_, tail_ = first["k1"][:3]
+                    made = [at_, totw_]
+                    if tail_ is not None:
+                        made += list(tail_) if isinstance(tail_, tuple) else [tail_]
+                    return made
                 fork = _nystrom.SideStream(launch_first, dev, part)
         with fork:
             U, Uext = self._basis(Z, n, kernel, spec, center, inv_ls, lm)
@@ -526,9 +541,12 @@ class Recombiner:
                 design, totw = ops.project_design(at, Uext, totw, tail=extra[:Lp], tail_tw=extra[Lp:Lp + 1])
                 bary = None
             else:
-                at[S - 1] += extra[:Lp]
-                totw = totw.clone()
-                totw[S - 1] += extra[Lp]
+                if fast_tail:
+                    totw = ops.apply_tail(at, totw, *(extra if extra is not None else (None, None)))
+                else:
+                    at[S - 1] += extra[:Lp]
+                    totw = totw.clone()
+                    totw[S - 1] += extra[Lp]
                 bary = at @ UextT                                   # (S x n)  == (U @ X_for_nys).T
                 if objs is not None:
                     objs[S - 1, 0] += extra[Lp + 1]

@@ -47,6 +47,17 @@ __global__ void __launch_bounds__(32 * PREP_RL) car_prepare_kernel(const double*
     }
 }
 
+// Second count of the remainder (SOBER/_rchq.py:153-164) folded into the group sums in one launch:
+//   at[S-1, :] += tail_at (tail_at may be NULL: no remainder on this call);  totw_out = totw_in, + tail_tw[0] at S-1.
+__global__ void __launch_bounds__(256) apply_tail_kernel(double* __restrict__ at_last, const double* __restrict__ tail_at,
+                                                         int Lp, const double* __restrict__ totw_in,
+                                                         const double* __restrict__ tail_tw, int S,
+                                                         double* __restrict__ totw_out) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (tail_at && i < Lp) at_last[i] += tail_at[i];
+    if (i < S) totw_out[i] = totw_in[i] + ((tail_tw && i == S - 1) ? tail_tw[0] : 0.0);
+}
+
 // After the elimination: poison the weights when the one-pass Cholesky-QR behind the projector was not accurate enough
 // (|Delta|_F >= 1e-5) or something is not finite, then the survivor bookkeeping the host reads with ONE copy:
 //   summary[i] = number of kept groups among 0..i (inclusive), summary[S] = 1 if all weights are finite, rank[i] =
@@ -129,6 +140,17 @@ extern "C" int sober_car_prepare(const double* F, int64_t ldf, const double* div
     if (!F || !out || S <= 0 || n < 0 || ldf < n || ldo < n + 1) return SOBER_ERR_ARG;
     car_prepare_kernel<<<(unsigned)ceil_div(n + 1, 32), 32 * PREP_RL, 0, (cudaStream_t)stream>>>(F, ldf, div, S, n, out, ldo);
     SOBER_LAUNCH_CHECK("car_prepare");
+    return SOBER_OK;
+}
+
+extern "C" int sober_apply_tail(double* at_last_row, const double* tail_at, int32_t Lp, const double* totw_in,
+                                const double* tail_tw, int32_t S, double* totw_out, void* stream) {
+    if (!at_last_row || !totw_in || !totw_out || S <= 0 || Lp <= 0 || (tail_at == nullptr) != (tail_tw == nullptr))
+        return SOBER_ERR_ARG;
+    const int n = S > Lp ? S : Lp;
+    apply_tail_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(at_last_row, tail_at, Lp, totw_in, tail_tw,
+                                                                                  S, totw_out);
+    SOBER_LAUNCH_CHECK("apply_tail");
     return SOBER_OK;
 }
 
