@@ -254,6 +254,15 @@ int sober_update_compact(const int32_t* idx_in, const double* mu_in, int64_t n_l
                          int32_t tail_keep, int64_t new_pos0, int32_t* idx_out, double* mu_out,
                          const double* rec_in, double* rec_out, int64_t ldr, int32_t d, void* stream);
 
+/* The same with K, tail_keep and new_pos0 taken on the DEVICE from ``summary`` (the inclusive cumulative kept-count of
+ * sober_car_summary): K = summary[S-1], tail_keep = K > summary[S-2], new_pos0 = number of survivors below pos0 (the
+ * closed form above).  Nothing here waits for the host, so the call can be enqueued right behind the Caratheodory step;
+ * the outputs must hold n_local entries (the number of survivors is not known to the host yet). */
+int sober_update_compact_dev(const int32_t* idx_in, const double* mu_in, int64_t n_local, int64_t pos0, int64_t ES,
+                             int32_t S, const double* wstar, const double* totw, const int32_t* rank,
+                             const int32_t* summary, int32_t* idx_out, double* mu_out, const double* rec_in,
+                             double* rec_out, int64_t ldr, int32_t d, void* stream);
+
 /* dst[:] = 0 ; dst[idx[j]] = w[j]   -- the in-place sparse result of SOBER/_rchq.py:109-110. */
 int sober_scatter_result(double* dst, int64_t n, const int64_t* idx, const double* w, int64_t m, void* stream);
 

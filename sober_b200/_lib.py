@@ -73,6 +73,8 @@ PROTOTYPES = {
     "sober_apply_tail": (C.c_int, [_P, _P, _I32, _P, _P, _I32, _P, _P]),
     "sober_update_compact": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _I32, _I32, _I64, _P, _P,
                                        _P, _P, _I64, _I32, _P]),
+    "sober_update_compact_dev": (C.c_int, [_P, _P, _I64, _I64, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32,
+                                           _P]),
     "sober_scatter_result": (C.c_int, [_P, _I64, _P, _P, _I64, _P]),
     "sober_project_design": (C.c_int, [_P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _I64, _P, _P]),
     "sober_trsm_right_upper": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _I64, _P]),

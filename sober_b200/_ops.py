@@ -421,6 +421,24 @@ class CudaOps:
         self.launches += 1
         return idx_out, mu_out, rec_out
 
+    def update_compact_dev(self, idx, mu, n_local, pos0, ES, S, wstar, totw, rank, summary, rec=None, d=0):
+        """``update_compact`` with the survivor counts read from ``summary`` on the device: no host value is needed, so
+        it is enqueued right behind the Caratheodory step.  Outputs hold n_local entries; the caller slices them once
+        it knows the number of survivors."""
+        idx_out = torch.empty(n_local, dtype=torch.int32, device=self.device)
+        mu_out = torch.empty(n_local, dtype=torch.float64, device=self.device)
+        ldr = 0 if rec is None else rec.stride(0)
+        rec_out = None if rec is None else torch.empty((n_local, ldr), dtype=torch.float64, device=self.device)
+        with self._guard():
+            t0 = self._begin("update_compact")
+            check(self.lib.sober_update_compact_dev(_ptr(idx), _ptr(mu), int(n_local), int(pos0), int(ES), int(S),
+                                                    _ptr(wstar), _ptr(totw), _ptr(rank), _ptr(summary), _ptr(idx_out),
+                                                    _ptr(mu_out), _ptr(rec), _ptr(rec_out), int(ldr), int(d),
+                                                    self._stream()), "update_compact_dev")
+            self._end("update_compact", t0, (12 + 8 * ldr) * int(n_local) * 3 // 2)   # work = HBM bytes (half survive)
+        self.launches += 1
+        return idx_out, mu_out, rec_out
+
     def scatter_result(self, dst, idx, w):
         with self._guard():
             check(self.lib.sober_scatter_result(_ptr(dst), dst.numel(), _ptr(idx), _ptr(w), idx.numel(),

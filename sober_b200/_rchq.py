@@ -560,16 +560,23 @@ class Recombiner:
             if design is None and not graph_step:
                 bary = bary / totw.unsqueeze(1)
             clock.lap("tail+project")
-            rank = keep = None
+            rank = keep = early = None
             n_design = (design.shape[1] if design is not None else bary.shape[1] + 1)
             if graph_step:
                 # the whole step (barycentres, null space, elimination, survivor counts and ranks) as one CUDA-graph replay
                 wfull, kept, summary, rank = _car.reduce_step(ops, bary, totw, use_graph=o.graphs and o.stats is None,
                                                               divide=True, comm=comm)
+                # the weight update + compaction is enqueued BEFORE the host reads the survivor counts: the kernel takes
+                # them from the device summary (closed form of KeepMap.before), so the GPU goes on while the host syncs
+                # and prepares the next K1 launch.  Discarded in the (rare) retry case.
+                if hasattr(ops, "update_compact_dev") and n_local > 0:
+                    early = ops.update_compact_dev(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, summary,
+                                                   rec=alive.rec, d=d)
                 summary = summary.tolist()                                               # the one host sync of the iteration
                 keep = KeepMap.from_summary(summary, S, ES)
                 retry = _car.needs_retry("projector", keep.K, n_design, bool(summary[S]))
                 if retry:
+                    early = None
                     bary = bary / totw.unsqueeze(1)
             else:
                 wfull = _car.caratheodory(ops, bary, totw, o.nullspace, self.nullspace, design=design)
@@ -595,8 +602,12 @@ class Recombiner:
                 keep = KeepMap(flags[:-1], S, ES)
             new_pos0 = keep.before(pos0)
             new_local = keep.before(pos0 + n_local) - new_pos0
-            alive = Alive(*ops.update_compact(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, keep.K,
-                                              keep.tail_keep, new_pos0, new_local, rec=alive.rec, d=d))
+            if early is not None:
+                alive = Alive(early[0][:new_local], early[1][:new_local],
+                              None if early[2] is None else early[2][:new_local])
+            else:
+                alive = Alive(*ops.update_compact(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, keep.K,
+                                                  keep.tail_keep, new_pos0, new_local, rec=alive.rec, d=d))
             pos0, n_local, remaining = new_pos0, new_local, keep.before(remaining)
             clock.lap("keepmap+update")
 

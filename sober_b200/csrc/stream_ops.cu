@@ -205,11 +205,25 @@ __global__ void __launch_bounds__(CP_THREADS) scatter_nonzero_kernel(const doubl
 constexpr int UC_THREADS = 256;
 constexpr int UC_ITEMS = 4;
 
+// ``summary`` (may be NULL): the inclusive cumulative kept-count of sober_car_summary.  With it the kernel derives K,
+// tail_keep and new_pos0 itself (the closed form the host uses, KeepMap.before), so it can be enqueued right behind the
+// Caratheodory step -- before the host has read the survivor counts.
 __global__ void __launch_bounds__(UC_THREADS) update_compact_kernel(
     const int32_t* __restrict__ idx_in, const double* __restrict__ mu_in, int64_t n_local, int64_t pos0, int64_t ES,
     int S, const double* __restrict__ wstar, const double* __restrict__ totw, const int32_t* __restrict__ rank, int K,
     int tail_keep, int64_t new_pos0, int32_t* __restrict__ idx_out, double* __restrict__ mu_out,
-    const double* __restrict__ rec_in, double* __restrict__ rec_out, int ldr, int d) {
+    const double* __restrict__ rec_in, double* __restrict__ rec_out, int ldr, int d,
+    const int32_t* __restrict__ summary) {
+    if (summary) {
+        K = summary[S - 1];
+        tail_keep = K > (S > 1 ? summary[S - 2] : 0);
+        if (pos0 <= ES) {
+            const int64_t r = pos0 % S;
+            new_pos0 = (pos0 / S) * K + (r > 0 ? summary[r - 1] : 0);
+        } else {
+            new_pos0 = (ES / S) * K + (tail_keep ? pos0 - ES : 0);
+        }
+    }
     const int64_t tile0 = (int64_t)blockIdx.x * (UC_THREADS * UC_ITEMS);
     const int64_t p_tile = pos0 + tile0;
     const int64_t e_tile = p_tile / S;                 // one 64-bit division per thread, not per element
@@ -376,8 +390,25 @@ extern "C" int sober_update_compact(const int32_t* idx_in, const double* mu_in, 
     const int64_t tile = UC_THREADS * UC_ITEMS;
     update_compact_kernel<<<(unsigned)ceil_div(n_local, tile), UC_THREADS, 0, (cudaStream_t)stream>>>(
         idx_in, mu_in, n_local, pos0, ES, S, wstar, totw, rank, K, tail_keep, new_pos0, idx_out, mu_out, rec_in, rec_out,
-        (int)ldr, d);
+        (int)ldr, d, nullptr);
     SOBER_LAUNCH_CHECK("update_compact");
+    return SOBER_OK;
+}
+
+extern "C" int sober_update_compact_dev(const int32_t* idx_in, const double* mu_in, int64_t n_local, int64_t pos0,
+                                        int64_t ES, int32_t S, const double* wstar, const double* totw,
+                                        const int32_t* rank, const int32_t* summary, int32_t* idx_out, double* mu_out,
+                                        const double* rec_in, double* rec_out, int64_t ldr, int32_t d, void* stream) {
+    if (n_local < 0 || S <= 0 || ES < 0 || ES % S != 0 || pos0 < 0 || !summary) return SOBER_ERR_ARG;
+    if (n_local == 0) return SOBER_OK;
+    if (!idx_in || !mu_in || !wstar || !totw || !rank || !idx_out || !mu_out) return SOBER_ERR_ARG;
+    if (pos0 + n_local >= ((int64_t)1 << 31)) return SOBER_ERR_UNSUPPORTED;
+    if (rec_in && (!rec_out || ldr < d + 2 || (ldr & 1))) return SOBER_ERR_ARG;
+    const int64_t tile = UC_THREADS * UC_ITEMS;
+    update_compact_kernel<<<(unsigned)ceil_div(n_local, tile), UC_THREADS, 0, (cudaStream_t)stream>>>(
+        idx_in, mu_in, n_local, pos0, ES, S, wstar, totw, rank, 0, 0, 0, idx_out, mu_out, rec_in, rec_out, (int)ldr, d,
+        summary);
+    SOBER_LAUNCH_CHECK("update_compact_dev");
     return SOBER_OK;
 }
 

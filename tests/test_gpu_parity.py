@@ -358,6 +358,11 @@ def test_update_compact_exact(ops, cuda_device, S, R, pos0):
     want_rec = rec[live].clone()
     want_rec[:, dim + 1] = want_mu
     assert torch.equal(rec_o.cpu(), want_rec)
+    # the device-driven variant (K, tail_keep, new_pos0 from the cumulative kept-count on the device): same bits
+    summary = torch.cat([torch.cumsum(kept.int(), 0).to(torch.int32), torch.ones(1, dtype=torch.int32)])
+    idx_d, mu_d, rec_d = ops.update_compact_dev(d(idx), d(mu), n_local, pos0, ES, S, d(wstar), d(totw), d(rank), d(summary),
+                                                rec=d(rec), d=dim)
+    assert torch.equal(idx_d[:n_out], idx_o) and torch.equal(mu_d[:n_out], mu_o) and torch.equal(rec_d[:n_out], rec_o)
 
 
 @pytest.mark.parametrize("n,d", [(1000, 6), (333, 2), (257, 24), (100, 300)])
