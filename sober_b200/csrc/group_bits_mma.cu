@@ -5,6 +5,10 @@
 // (group_bits_kernel), whose 16 POPC per clock per SM bound C4 at 84 ms per step.  Replaces SOBER/_rchq.py:124-136 for
 // SOBER/_drug_modelling.py:15-25 exactly like the other K1 kernels (same contract: At, totw, the remainder quirk).
 //
+// Two kernels.  The DEFAULT is version 2 (group_bits_mma2_kernel, second half of this file: landmark tile resident in
+// TMEM as the A operand, loader / expander / MMA / epilogue warps).  Version 1 below (landmark tile resident in shared
+// memory) is kept for comparison (variant 5):
+//
 // CTA = 128 groups (one candidate per group and row) x 64 landmarks.  Warp roles:
 //   warps 0-3  EXPANDERS  thread r owns candidate row r of the current row: gathers its bit-packed words from HBM
 //                         (128 B per 1024-bit fingerprint: HBM traffic stays that of the packed format) and expands them
@@ -292,8 +296,11 @@ __global__ void __launch_bounds__(BM_THREADS, 1) group_bits_mma_kernel(const Bit
 // columns at d = 1024) and only the streamed candidate tile (B: 64 candidates x 256 K-elements per stage, 16 KB) passes
 // through shared memory: 64 KB stored + 64 KB read by the tensor core per 128 x 64 tile, and each candidate row is
 // expanded by L / 128 CTAs instead of L / 64.  The epilogue thread is now a LANDMARK (TMEM lane) and walks the tile's
-// candidates (accumulator columns): its 32 FP64 accumulators are the groups g0 + 32 h + j, stores to At are coalesced
-// along the landmarks.  TMEM: 256 columns A + 2 x 64 columns of int32 accumulators (512 allocated).
+// candidates (accumulator columns): 16 epilogue warps (4 column groups per lane quarter), 16 FP64 accumulators per
+// thread, stores to At coalesced along the landmarks.  TMEM: 256 columns A + 2 x 64 columns of int32 accumulators (512
+// allocated).  Warps: 0-7 expanders (4 threads per candidate row), 8-23 epilogue, 24 MMA (whole warp runs the loop, an
+// elected lane issues), 25-26 loaders (lane = candidate row, cp.async staging ring).  Two 64 KB operand slots, one
+// fence.proxy.async per tile and thread.  What each design step bought, with the ncu readings: profiles/r02_bits_tcgen05.txt
 // =====================================================================================================
 constexpr int B2_TN = 64;         // candidates (groups) per tile = accumulator columns
 constexpr int B2_TM = 128;        // landmarks per CTA = TMEM lanes
