@@ -131,22 +131,42 @@ class Alive:
 
 
 class _StageClock:
-    """Optional per-stage wall clock (``options.stats = {}``): synchronises the device at every stage boundary, so it
-    is a diagnostic, not something to leave on when timing the whole call."""
+    """Stage boundaries of one call.  ``options.stats = {}``: per-stage wall clock -- synchronises the device at every
+    boundary, so it is a diagnostic, not something to leave on when timing the whole call.  ``options.nvtx`` (env
+    SOBER_B200_NVTX=1): an NVTX range per stage instead ("sober_b200/k1", "sober_b200/car", ...; no synchronisation), for
+    ``ncu --nvtx --nvtx-include`` / Nsight Systems timelines."""
 
-    def __init__(self, sink, device):
+    _NEXT = {"setup": "compact+records", "compact+records": "nystrom", "nystrom": "k1 | finish", "k1": "tail+project",
+             "tail+project": "car", "car": "keepmap+update", "keepmap+update": "k1 | finish", "finish": None}
+
+    def __init__(self, sink, device, nvtx=False):
         self.sink, self.device, self.t = sink, device, None
+        self.nvtx = bool(nvtx) and device.type == "cuda"
         if sink is not None and device.type == "cuda":
             torch.cuda.synchronize(device)
             self.t = time.perf_counter()
+        if self.nvtx:
+            torch.cuda.nvtx.range_push("sober_b200/setup")
 
     def lap(self, name):
+        if self.nvtx:
+            torch.cuda.nvtx.range_pop()
+            nxt = self._NEXT.get(name)
+            if nxt is not None:
+                torch.cuda.nvtx.range_push("sober_b200/" + nxt)
+            else:
+                self.nvtx = False
         if self.t is None:
             return
         torch.cuda.synchronize(self.device)
         now = time.perf_counter()
         self.sink[name] = self.sink.get(name, 0.0) + (now - self.t) * 1e3
         self.t = now
+
+    def close(self):
+        if self.nvtx:
+            torch.cuda.nvtx.range_pop()
+            self.nvtx = False
 
 
 class Recombiner:
@@ -331,7 +351,7 @@ class Recombiner:
                 clearing = threading.Thread(target=_clear, daemon=True)
                 clearing.start()
 
-        clock = _StageClock(o.stats, dev)
+        clock = _StageClock(o.stats, dev, getattr(o, "nvtx", False))
         spec = introspect(kernel) if o.fuse else None
         if spec is not None and spec.d is not None and spec.d != X.shape[1]:
             raise ValueError("lengthscale dimension does not match the inputs")

@@ -53,6 +53,7 @@ class Options:
         self.car_kernel = os.environ.get("SOBER_B200_CAR", "panel")   # "panel": blocked row-distributed cluster kernel
                                       # (csrc/car_panel.cu) for the fused-arithmetic elimination; "legacy": round-1 kernels
         self.car_panel_nb = int(os.environ.get("SOBER_B200_CAR_NB", "0"))   # 0 = automatic panel width
+        self.nvtx = os.environ.get("SOBER_B200_NVTX", "0") != "0"           # an NVTX range per stage of recombination()
         # multi-GPU: from this many groups S on, the projector null space of the replicated Caratheodory step is split
         # over the ranks (_car.projector_rows_sharded, 4 collectives per call).  OFF by default: measured at C5
         # (S = 2002) on 2 and 8 GPUs the step takes the same 1.6 ms either way -- it is bound by the latency of the
