@@ -31,6 +31,7 @@ for step in "$@"; do
     sanit)    TMO=900 TAILN=12 run sanitizer_racecheck compute-sanitizer --tool racecheck --print-limit 5 python -m pytest tests/test_car_panel.py tests/test_bits_mma.py -x -q -m gpu -k "400-200-0 or 130-61-64 or early_stop or 256-0.1" ;
               TMO=900 TAILN=12 run sanitizer_memcheck compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_car_panel.py tests/test_bits_mma.py tests/test_pi.py -x -q -m gpu -k "400-200-0 or 1000-500-0 or early_stop or 256-0.1 or 12_345 or pi_rbf" ;;
     sanitbits) TMO=900 TAILN=30 run sanitizer_racecheck_bits compute-sanitizer --tool racecheck --print-limit 40 python -m pytest tests/test_bits_mma.py -x -q -m gpu -k "256-0.1 or 4_100 or 12_345" ;;
+    sanitall) TMO=1500 TAILN=15 run sanitizer_memcheck_suite compute-sanitizer --tool memcheck --print-limit 10 python -m pytest tests -x -q -m gpu -k "not full_size and not pipelined and not sharded and not at_size and not car_cluster and not cholesky" ;;
     ncustep)  TMO=900 TAILN=3 run ncu_step ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_c2.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras ;;
     bench1)   TMO=600 TAILN=3 run bench_c1 python bench.py --workload c1 --steps 10 --warmup 3 ;;
     stagepar) TAILN=25 run stage_c2_parity python tools/stage_breakdown.py c2 parity ;;
