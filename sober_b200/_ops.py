@@ -392,6 +392,32 @@ class CudaOps:
         self.launches += 1
         return summary, rank
 
+    def fetch_small(self, t):
+        """Start a device-to-host copy of the small tensor ``t`` (as it is NOW in stream order) on a side stream into pinned
+        memory; returns a function that waits for that copy alone and gives the values as a list.  Work enqueued on the
+        current stream after this call is not waited for."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_fetch_stream", None) is None:
+            self._fetch_stream = torch.cuda.Stream(self.device)
+            self._fetch_buf = {}
+        key = (t.dtype, t.numel())
+        host = self._fetch_buf.get(key)
+        if host is None:
+            host = self._fetch_buf[key] = torch.empty(t.numel(), dtype=t.dtype).pin_memory()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side = self._fetch_stream
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            host.copy_(t.reshape(-1), non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+
+        def wait():
+            done.synchronize()
+            return host.tolist()
+        return wait
+
     def apply_tail(self, at, totw, tail_at=None, tail_tw=None):
         """at[S-1] += tail_at (in place) and a copy of ``totw`` with tail_tw added to its last entry: the second count of
         the remainder (SOBER/_rchq.py:153-164) in one launch.  Without a remainder: just the copy."""

@@ -590,9 +590,14 @@ class Recombiner:
                 # them from the device summary (closed form of KeepMap.before), so the GPU goes on while the host syncs
                 # and prepares the next K1 launch.  Discarded in the (rare) retry case.
                 if hasattr(ops, "update_compact_dev") and n_local > 0:
+                    # ... and the counts travel to the host on a side stream that waits for the Caratheodory step only,
+                    # not for the update kernel behind it
+                    fetch = ops.fetch_small(summary) if hasattr(ops, "fetch_small") else None
                     early = ops.update_compact_dev(idx, mass, n_local, pos0, ES, S, wfull, totw, rank, summary,
                                                    rec=alive.rec, d=d)
-                summary = summary.tolist()                                               # the one host sync of the iteration
+                    summary = fetch() if fetch is not None else summary.tolist()
+                else:
+                    summary = summary.tolist()                                           # the one host sync of the iteration
                 keep = KeepMap.from_summary(summary, S, ES)
                 retry = _car.needs_retry("projector", keep.K, n_design, bool(summary[S]))
                 if retry:
